@@ -1,0 +1,728 @@
+// libfmt_b200.so - host side of the C ABI declared in include/fmt_b200.h.
+//
+// Owns: the packed weights (bf16 for the tcgen05 path + fp32 for the validation mode), the workspace, the per-plan
+// CUDA graph of one sampling window, and the window loop of _perform_ode_sampling_loop (nodes_adv.py:545-694),
+// which runs entirely on the device: windows are chained through prev_x / prev_wa / prev_we without host syncs.
+#include "../../include/fmt_b200.h"
+#include "kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace fmt;
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static int set_err(int code, const char* fmtstr, ...) {
+  va_list ap;
+  va_start(ap, fmtstr);
+  vsnprintf(g_err, sizeof(g_err), fmtstr, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_OK(expr)                                                                                         \
+  do {                                                                                                        \
+    cudaError_t _e = (expr);                                                                                  \
+    if (_e != cudaSuccess) return set_err(-2, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define FMT_OK(expr)          \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != 0) return _r;   \
+  } while (0)
+#define REQUIRE(cond, ...)                          \
+  do {                                              \
+    if (!(cond)) return set_err(-1, __VA_ARGS__);   \
+  } while (0)
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// ------------------------------------------------------------------------------------------------ handle
+struct Linear {
+  bf16* w16 = nullptr;    // (N, K) bf16, K possibly padded
+  float* w32 = nullptr;   // (N, K) fp32 (validation mode)
+  float* b = nullptr;     // (N)
+  int N = 0, K = 0;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct FmtHandle {
+  int device = 0;
+  int num_sms = 148;
+  FmtDims d{};
+  int N = 0, Kc = 0, NT = 0;
+  PFN_encodeTiled encode = nullptr;
+
+  Linear x_emb, c_emb, ada, dec;
+  std::vector<Linear> qkv, proj, fc1, fc2;
+  float *t0_w = nullptr, *t0_b = nullptr, *t2_w = nullptr, *t2_b = nullptr, *pos = nullptr;
+  std::vector<void*> owned;
+
+  // plan
+  bool configured = false;
+  FmtPlan plan{};
+  std::vector<float> t_eval, dt, rk_a, rk_b;
+  ModelShape shape{};
+  int R = 0, U = 0, n_eval = 0, table_chunk = 0;
+  size_t tsize = 2;   // sizeof(activation type)
+
+  // workspace
+  DevBuf cond, cemb, temb, tfreq, th, silu, table, xstate, ystage, kbuf, prevx, ax, X, A1, QKV, A2, Hm, V, ddt, dteval, wargs;
+  DevBuf st_rs, st_wa, st_we, st_noise, st_rd;   // staging for host-located clips
+  size_t ws_bytes = 0;
+
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_nodes = 0;
+  long long launches = 0;
+  bool capturing = false;
+  long long capture_launches = 0;
+};
+
+static int dev_alloc(FmtHandle* h, DevBuf& b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return 0;
+  if (b.p) {
+    CUDA_OK(cudaFree(b.p));
+    h->ws_bytes -= b.bytes;
+    b.p = nullptr;
+    b.bytes = 0;
+  }
+  bytes = (bytes + 255) & ~static_cast<size_t>(255);
+  CUDA_OK(cudaMalloc(&b.p, bytes));
+  b.bytes = bytes;
+  h->ws_bytes += bytes;
+  return 0;
+}
+
+static inline void count_launch(FmtHandle* h) {
+  if (h->capturing) h->capture_launches++;
+  else h->launches++;
+}
+#define LAUNCH_CHECK() CUDA_OK(cudaGetLastError())
+
+// ------------------------------------------------------------------------------------------------ GEMM launch
+static int make_tmap(FmtHandle* h, CUtensorMap* m, const void* ptr, int rows, int cols, int ld_elems, int box_rows) {
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(-3, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d box=%d ptr=%p", (int)r, rows, cols, ld_elems, box_rows, ptr);
+  return 0;
+}
+
+template <int BN>
+static int launch_tc(FmtHandle* h, const bf16* A, int lda, const bf16* W, int ldw, const EpiParams& ep, int K, cudaStream_t st) {
+  using C = TcCfg<BN>;
+  static bool attr_set[64] = {};
+  if (!attr_set[h->device & 63]) {   // per device: the attribute lives in the device's module image
+    CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set[h->device & 63] = true;
+  }
+  CUtensorMap ta, tb;
+  FMT_OK(make_tmap(h, &ta, A, ep.M, K, lda, C::BM));
+  FMT_OK(make_tmap(h, &tb, W, ep.N, K, ldw, BN));
+  const int tiles = ((ep.M + C::BM - 1) / C::BM) * ((ep.N + BN - 1) / BN);
+  const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+  gemm_tc_kernel<BN, bf16><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, ep, K);
+  LAUNCH_CHECK();
+  count_launch(h);
+  return 0;
+}
+
+static int pick_bn(const FmtHandle* h, int M, int N) {
+  const int mt = (M + 127) / 128;
+  if (N % 256 == 0 && mt * (N / 256) >= 2 * h->num_sms) return 256;
+  if (N % 128 == 0 && mt * (N / 128) >= h->num_sms) return 128;
+  return 64;
+}
+
+static int gemm_bf16(FmtHandle* h, const bf16* A, int lda, const bf16* W, int ldw, const EpiParams& ep, int K, cudaStream_t st, int force_bn = 0) {
+  REQUIRE(ep.N % 32 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm_bf16: N %% 32, K/lda/ldw %% 8 required (N=%d K=%d)", ep.N, K);
+  const int bn = force_bn ? force_bn : pick_bn(h, ep.M, ep.N);
+  switch (bn) {
+    case 256: return launch_tc<256>(h, A, lda, W, ldw, ep, K, st);
+    case 128: return launch_tc<128>(h, A, lda, W, ldw, ep, K, st);
+    case 64: return launch_tc<64>(h, A, lda, W, ldw, ep, K, st);
+  }
+  return set_err(-1, "gemm_bf16: block_n must be 64, 128 or 256 (got %d)", bn);
+}
+
+static int gemm_f32(FmtHandle* h, const float* A, int lda, const float* W, int ldw, const EpiParams& ep, int K, cudaStream_t st) {
+  REQUIRE(ep.N % 4 == 0 && K % 16 == 0 && lda % 4 == 0 && ldw % 4 == 0, "gemm_f32: N %% 4, K %% 16 required (N=%d K=%d)", ep.N, K);
+  dim3 grid((ep.N + 63) / 64, (ep.M + 63) / 64);
+  gemm_simt_kernel<<<grid, 256, 0, st>>>(A, lda, W, ldw, ep, K);
+  LAUNCH_CHECK();
+  count_launch(h);
+  return 0;
+}
+
+template <typename T> struct ModeOps;
+template <> struct ModeOps<bf16> {
+  static int gemm(FmtHandle* h, const void* A, int lda, const Linear& L, const EpiParams& ep, cudaStream_t st) {
+    return gemm_bf16(h, static_cast<const bf16*>(A), lda, L.w16, L.K, ep, L.K, st);
+  }
+};
+template <> struct ModeOps<float> {
+  static int gemm(FmtHandle* h, const void* A, int lda, const Linear& L, const EpiParams& ep, cudaStream_t st) {
+    return gemm_f32(h, static_cast<const float*>(A), lda, L.w32, L.K, ep, L.K, st);
+  }
+};
+
+static EpiParams epi(int kind, int M, int N, const float* bias, void* out, int ldo, int out_f32) {
+  EpiParams p{};
+  p.kind = kind; p.M = M; p.N = N; p.bias = bias; p.out = out; p.ldo = ldo; p.out_f32 = out_f32;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------ the FMT step
+template <typename T>
+static int enqueue_prepare(FmtHandle* h, cudaStream_t st) {
+  const ModelShape& s = h->shape;
+  const WindowArgs* wa = static_cast<const WindowArgs*>(h->wargs.p);
+  cond_gather_kernel<T><<<h->U, 128, 0, st>>>(wa, s, static_cast<T*>(h->cond.p));
+  LAUNCH_CHECK(); count_launch(h);
+  EpiParams ep = epi(EPI_STORE, h->U, s.H, h->c_emb.b, h->cemb.p, s.H, 1);
+  FMT_OK(ModeOps<T>::gemm(h, h->cond.p, s.Kc, h->c_emb, ep, st));
+  return 0;
+}
+
+// AdaLN tables for evaluations [e0, e0+n): table[(e-e0)*U + u, :] = Linear_ada(SiLU(c_emb[u] + t_emb[e]))
+template <typename T>
+static int enqueue_tables(FmtHandle* h, int e0, int n, cudaStream_t st) {
+  const ModelShape& s = h->shape;
+  const size_t total = static_cast<size_t>(n) * h->U * s.H;
+  silu_cond_kernel<T><<<static_cast<unsigned>((total / 4 + 255) / 256), 256, 0, st>>>(
+      static_cast<const float*>(h->cemb.p), static_cast<const float*>(h->temb.p), e0, h->U, s.H, static_cast<T*>(h->silu.p), total);
+  LAUNCH_CHECK(); count_launch(h);
+  EpiParams ep = epi(EPI_STORE, n * h->U, h->NT, h->ada.b, h->table.p, h->NT, 0);
+  FMT_OK(ModeOps<T>::gemm(h, h->silu.p, s.H, h->ada, ep, st));
+  return 0;
+}
+
+template <typename T>
+static int launch_lnmod(FmtHandle* h, const T* table_e, long long shift_off, long long scale_off, cudaStream_t st) {
+  const ModelShape& s = h->shape;
+  const int warps = 8;
+  lnmod_kernel<T, T><<<(h->R + warps - 1) / warps, warps * 32, 0, st>>>(static_cast<const float*>(h->X.p), h->R, s.H, table_e, nullptr,
+                                                                        h->NT, shift_off, scale_off, static_cast<T*>(h->A1.p));
+  LAUNCH_CHECK(); count_launch(h);
+  return 0;
+}
+
+template <typename T>
+static int launch_attn(FmtHandle* h, cudaStream_t st) {
+  const ModelShape& s = h->shape;
+  const int heads = h->d.num_heads, hd = s.H / heads;
+  const int n_seq = s.nb * s.B, total_warps = n_seq * heads * s.N, warps = 8;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  const unsigned grid = (total_warps + warps - 1) / warps;
+  const T* qkv = static_cast<const T*>(h->QKV.p);
+  T* out = static_cast<T*>(h->A2.p);
+  switch (hd) {
+    case 32: band_attention_kernel<T, 1><<<grid, warps * 32, 0, st>>>(qkv, n_seq, s.N, heads, h->d.attention_window, scale, out); break;
+    case 64: band_attention_kernel<T, 2><<<grid, warps * 32, 0, st>>>(qkv, n_seq, s.N, heads, h->d.attention_window, scale, out); break;
+    case 128: band_attention_kernel<T, 4><<<grid, warps * 32, 0, st>>>(qkv, n_seq, s.N, heads, h->d.attention_window, scale, out); break;
+    default: return set_err(-1, "head_dim %d unsupported (32, 64, 128)", hd);
+  }
+  LAUNCH_CHECK(); count_launch(h);
+  return 0;
+}
+
+// One model evaluation: V[R, W] = FMT.forward over the nb-way batched CFG branches (FMT.py:277-340), inputs y (B,L,W).
+template <typename T>
+static int enqueue_forward(FmtHandle* h, int table_slot, const float* y, cudaStream_t st) {
+  const ModelShape& s = h->shape;
+  const FmtDims& d = h->d;
+  const WindowArgs* wa = static_cast<const WindowArgs*>(h->wargs.p);
+  const int R = h->R, H = s.H;
+  const T* table_e = static_cast<const T*>(h->table.p) + static_cast<size_t>(table_slot) * h->U * h->NT;
+
+  pack_x_kernel<T><<<s.B * s.N, 128, 0, st>>>(wa, s, y, static_cast<const float*>(h->prevx.p), static_cast<T*>(h->ax.p));
+  LAUNCH_CHECK(); count_launch(h);
+  {
+    EpiParams ep = epi(EPI_POS, R, H, h->x_emb.b, h->X.p, H, 1);
+    ep.pos = h->pos; ep.frames = s.N;
+    FMT_OK(ModeOps<T>::gemm(h, h->ax.p, s.W, h->x_emb, ep, st));
+  }
+  for (int i = 0; i < d.depth; ++i) {
+    const long long base = static_cast<long long>(i) * 6 * H;
+    FMT_OK(launch_lnmod<T>(h, table_e, base + 0, base + H, st));
+    FMT_OK(ModeOps<T>::gemm(h, h->A1.p, H, h->qkv[i], epi(EPI_STORE, R, 3 * H, h->qkv[i].b, h->QKV.p, 3 * H, 0), st));
+    FMT_OK(launch_attn<T>(h, st));
+    {
+      EpiParams ep = epi(EPI_GATE_RES, R, H, h->proj[i].b, h->X.p, H, 1);
+      ep.gate = table_e; ep.urow = nullptr; ep.ldg = h->NT; ep.gate_off = base + 2 * H;
+      FMT_OK(ModeOps<T>::gemm(h, h->A2.p, H, h->proj[i], ep, st));
+    }
+    FMT_OK(launch_lnmod<T>(h, table_e, base + 3 * H, base + 4 * H, st));
+    FMT_OK(ModeOps<T>::gemm(h, h->A1.p, H, h->fc1[i], epi(EPI_GELU, R, d.mlp_hidden, h->fc1[i].b, h->Hm.p, d.mlp_hidden, 0), st));
+    {
+      EpiParams ep = epi(EPI_GATE_RES, R, H, h->fc2[i].b, h->X.p, H, 1);
+      ep.gate = table_e; ep.urow = nullptr; ep.ldg = h->NT; ep.gate_off = base + 5 * H;
+      FMT_OK(ModeOps<T>::gemm(h, h->Hm.p, d.mlp_hidden, h->fc2[i], ep, st));
+    }
+  }
+  const long long dbase = static_cast<long long>(d.depth) * 6 * H;
+  FMT_OK(launch_lnmod<T>(h, table_e, dbase, dbase + H, st));
+  FMT_OK(ModeOps<T>::gemm(h, h->A1.p, H, h->dec, epi(EPI_STORE, R, s.W, h->dec.b, h->V.p, s.W, 1), st));
+  return 0;
+}
+
+static int launch_combine(FmtHandle* h, int mode, float* dst, const float* dt_ptr, cudaStream_t st) {
+  const ModelShape& s = h->shape;
+  const size_t n = static_cast<size_t>(s.B) * s.N * s.W;
+  cfg_combine_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(static_cast<const WindowArgs*>(h->wargs.p), s,
+                                                                            static_cast<const float*>(h->V.p), mode, dst, dt_ptr);
+  LAUNCH_CHECK(); count_launch(h);
+  return 0;
+}
+
+// The whole window: prepare -> tables -> S steps x stages -> finalize.  This is what gets captured in the graph.
+template <typename T>
+static int enqueue_window(FmtHandle* h, cudaStream_t st) {
+  const ModelShape& s = h->shape;
+  const WindowArgs* wa = static_cast<const WindowArgs*>(h->wargs.p);
+  const size_t nx = static_cast<size_t>(s.B) * s.L * s.W, nprev = static_cast<size_t>(s.B) * s.P * s.W;
+  float* x_state = static_cast<float*>(h->xstate.p);
+  float* y_stage = static_cast<float*>(h->ystage.p);
+  float* kbuf = static_cast<float*>(h->kbuf.p);
+  const float* ddt = static_cast<const float*>(h->ddt.p);
+  const int S = h->plan.n_steps, G = h->plan.n_stages;
+
+  init_window_kernel<<<static_cast<unsigned>((nx + 255) / 256), 256, 0, st>>>(wa, x_state, nx, static_cast<float*>(h->prevx.p), nprev);
+  LAUNCH_CHECK(); count_launch(h);
+  if (S > 0) FMT_OK(enqueue_prepare<T>(h, st));
+  for (int step = 0; step < S; ++step) {
+    for (int g = 0; g < G; ++g) {
+      const int e = step * G + g;
+      if (e % h->table_chunk == 0) {
+        const int n = (h->n_eval - e) < h->table_chunk ? (h->n_eval - e) : h->table_chunk;
+        FMT_OK(enqueue_tables<T>(h, e, n, st));
+      }
+      const float* y_in = x_state;
+      if (g > 0) {   // y_g = y0 + dt * sum_j a[g][j] k_j
+        const float* a = &h->rk_a[g * G];
+        rk_combine_kernel<<<static_cast<unsigned>((nx + 255) / 256), 256, 0, st>>>(x_state, y_stage, kbuf, nx, nx, g, a[0], G > 1 ? a[1] : 0.f,
+                                                                                  G > 2 ? a[2] : 0.f, G > 3 ? a[3] : 0.f, ddt + step);
+        LAUNCH_CHECK(); count_launch(h);
+        y_in = y_stage;
+      }
+      FMT_OK(enqueue_forward<T>(h, e % h->table_chunk, y_in, st));
+      if (G == 1) FMT_OK(launch_combine(h, 2, x_state, ddt + step, st));           // fused CFG + Euler
+      else FMT_OK(launch_combine(h, 1, kbuf + static_cast<size_t>(g) * nx, nullptr, st));
+    }
+    if (G > 1) {
+      const float* b = h->rk_b.data();
+      rk_combine_kernel<<<static_cast<unsigned>((nx + 255) / 256), 256, 0, st>>>(x_state, x_state, kbuf, nx, nx, G, b[0], G > 1 ? b[1] : 0.f,
+                                                                                G > 2 ? b[2] : 0.f, G > 3 ? b[3] : 0.f, ddt + step);
+      LAUNCH_CHECK(); count_launch(h);
+    }
+  }
+  finalize_window_kernel<<<static_cast<unsigned>((nx + 255) / 256), 256, 0, st>>>(wa, s, x_state, static_cast<float*>(h->prevx.p));
+  LAUNCH_CHECK(); count_launch(h);
+  return 0;
+}
+
+static int enqueue_window_mode(FmtHandle* h, cudaStream_t st) {
+  return h->plan.mode == FMT_MODE_BF16 ? enqueue_window<bf16>(h, st) : enqueue_window<float>(h, st);
+}
+
+// ------------------------------------------------------------------------------------------------ create / destroy
+static int upload(FmtHandle* h, const void* src, size_t n_floats, int location, float** out) {
+  float* p = nullptr;
+  CUDA_OK(cudaMalloc(&p, n_floats * sizeof(float)));
+  h->owned.push_back(p);
+  CUDA_OK(cudaMemcpy(p, src, n_floats * sizeof(float), location == FMT_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
+  *out = p;
+  return 0;
+}
+
+static int make_linear(FmtHandle* h, Linear& L, const void* w, const void* b, int N, int K, int Kpad, int location) {
+  float *w_raw = nullptr;
+  FMT_OK(upload(h, w, static_cast<size_t>(N) * K, location, &w_raw));
+  FMT_OK(upload(h, b, N, location, &L.b));
+  L.N = N; L.K = Kpad;
+  const size_t n = static_cast<size_t>(N) * Kpad;
+  CUDA_OK(cudaMalloc(&L.w16, n * sizeof(bf16)));
+  h->owned.push_back(L.w16);
+  pack_weight_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(w_raw, N, K, L.w16, Kpad);
+  LAUNCH_CHECK();
+  if (Kpad == K) {
+    L.w32 = w_raw;
+  } else {
+    CUDA_OK(cudaMalloc(&L.w32, n * sizeof(float)));
+    h->owned.push_back(L.w32);
+    pad_weight_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(w_raw, N, K, L.w32, Kpad);
+    LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" {
+
+int32_t fmt_abi_version(void) { return FMT_ABI_VERSION; }
+const char* fmt_last_error(void) { return g_err; }
+
+int32_t fmt_create(const FmtDims* dims, const void* const* wp, int32_t n_ptrs, int32_t location, int32_t device, FmtHandle** out) {
+  REQUIRE(dims && wp && out, "fmt_create: null argument");
+  const FmtDims& d = *dims;
+  REQUIRE(n_ptrs == FMT_W_NUM_GLOBAL + d.depth * FMT_W_PER_BLOCK, "fmt_create: expected %d weight pointers, got %d",
+          FMT_W_NUM_GLOBAL + d.depth * FMT_W_PER_BLOCK, n_ptrs);
+  for (int i = 0; i < n_ptrs; ++i) REQUIRE(wp[i] != nullptr, "fmt_create: weight pointer %d is null", i);
+  REQUIRE(d.dim_h % 128 == 0 && d.dim_w % 64 == 0 && d.dim_a % 4 == 0 && d.mlp_hidden % 64 == 0,
+          "fmt_create: unsupported dims (dim_h %% 128, dim_w %% 64, mlp_hidden %% 64 required)");
+  REQUIRE(d.dim_h % d.num_heads == 0, "fmt_create: dim_h must be divisible by num_heads");
+  const int hd = d.dim_h / d.num_heads;
+  REQUIRE(hd == 32 || hd == 64 || hd == 128, "fmt_create: head_dim %d unsupported (32, 64, 128)", hd);
+  REQUIRE(d.num_prev_frames <= d.frames_per_clip && d.num_prev_frames >= 0 && d.frames_per_clip > 0, "fmt_create: need 0 <= P <= L");
+  REQUIRE(d.attention_window >= 0, "fmt_create: attention_window must be >= 0");
+
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+    return set_err(-4, "fmt_create: no CUDA device - this library has no CPU fallback");
+  REQUIRE(device >= 0 && device < n_dev, "fmt_create: device %d out of range (%d devices)", device, n_dev);
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return set_err(-4, "fmt_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+  CUDA_OK(cudaSetDevice(device));
+
+  FmtHandle* h = new FmtHandle();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->d = d;
+  h->N = d.num_prev_frames + d.frames_per_clip;
+  h->Kc = ((d.dim_w + d.dim_a + d.dim_e + 63) / 64) * 64;
+  h->NT = d.depth * 6 * d.dim_h + 2 * d.dim_h;
+  {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+      delete h;
+      return set_err(-3, "fmt_create: cuTensorMapEncodeTiled not available from the driver");
+    }
+    h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  }
+  const int H = d.dim_h;
+  int rc = 0;
+#define TRY(expr) do { rc = (expr); if (rc != 0) { fmt_destroy(h); return rc; } } while (0)
+  TRY(make_linear(h, h->x_emb, wp[FMT_W_X_W], wp[FMT_W_X_B], H, d.dim_w, d.dim_w, location));
+  TRY(make_linear(h, h->c_emb, wp[FMT_W_C_W], wp[FMT_W_C_B], H, d.dim_w + d.dim_a + d.dim_e, h->Kc, location));
+  TRY(make_linear(h, h->dec, wp[FMT_W_DEC_W], wp[FMT_W_DEC_B], d.dim_w, H, H, location));
+  TRY(upload(h, wp[FMT_W_T0_W], static_cast<size_t>(H) * 256, location, &h->t0_w));
+  TRY(upload(h, wp[FMT_W_T0_B], H, location, &h->t0_b));
+  TRY(upload(h, wp[FMT_W_T2_W], static_cast<size_t>(H) * H, location, &h->t2_w));
+  TRY(upload(h, wp[FMT_W_T2_B], H, location, &h->t2_b));
+  TRY(upload(h, wp[FMT_W_POS], static_cast<size_t>(h->N) * H, location, &h->pos));
+  h->qkv.resize(d.depth); h->proj.resize(d.depth); h->fc1.resize(d.depth); h->fc2.resize(d.depth);
+  // concatenated AdaLN projection: rows [block0 (6H) | ... | block{depth-1} (6H) | decoder (2H)]
+  {
+    Linear& A = h->ada;
+    A.N = h->NT; A.K = H;
+    const size_t n = static_cast<size_t>(h->NT) * H;
+    cudaError_t e1 = cudaMalloc(&A.w32, n * sizeof(float));
+    cudaError_t e2 = cudaMalloc(&A.w16, n * sizeof(bf16));
+    cudaError_t e3 = cudaMalloc(&A.b, static_cast<size_t>(h->NT) * sizeof(float));
+    if (A.w32) h->owned.push_back(A.w32);
+    if (A.w16) h->owned.push_back(A.w16);
+    if (A.b) h->owned.push_back(A.b);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { fmt_destroy(h); return set_err(-2, "fmt_create: cudaMalloc failed for the AdaLN table weights"); }
+  }
+  const cudaMemcpyKind kind = location == FMT_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  for (int i = 0; i < d.depth; ++i) {
+    const void* const* bp = wp + FMT_W_NUM_GLOBAL + i * FMT_W_PER_BLOCK;
+    TRY(make_linear(h, h->qkv[i], bp[FMT_WB_QKV_W], bp[FMT_WB_QKV_B], 3 * H, H, H, location));
+    TRY(make_linear(h, h->proj[i], bp[FMT_WB_PROJ_W], bp[FMT_WB_PROJ_B], H, H, H, location));
+    TRY(make_linear(h, h->fc1[i], bp[FMT_WB_FC1_W], bp[FMT_WB_FC1_B], d.mlp_hidden, H, H, location));
+    TRY(make_linear(h, h->fc2[i], bp[FMT_WB_FC2_W], bp[FMT_WB_FC2_B], H, d.mlp_hidden, d.mlp_hidden, location));
+    if (cudaMemcpy(h->ada.w32 + static_cast<size_t>(i) * 6 * H * H, bp[FMT_WB_ADA_W], static_cast<size_t>(6) * H * H * sizeof(float), kind) != cudaSuccess ||
+        cudaMemcpy(h->ada.b + static_cast<size_t>(i) * 6 * H, bp[FMT_WB_ADA_B], static_cast<size_t>(6) * H * sizeof(float), kind) != cudaSuccess) {
+      fmt_destroy(h);
+      return set_err(-2, "fmt_create: copying adaLN weights of block %d failed", i);
+    }
+  }
+  if (cudaMemcpy(h->ada.w32 + static_cast<size_t>(d.depth) * 6 * H * H, wp[FMT_W_DEC_ADA_W], static_cast<size_t>(2) * H * H * sizeof(float), kind) != cudaSuccess ||
+      cudaMemcpy(h->ada.b + static_cast<size_t>(d.depth) * 6 * H, wp[FMT_W_DEC_ADA_B], static_cast<size_t>(2) * H * sizeof(float), kind) != cudaSuccess) {
+    fmt_destroy(h);
+    return set_err(-2, "fmt_create: copying decoder adaLN weights failed");
+  }
+  {
+    const size_t n = static_cast<size_t>(h->NT) * H;
+    pack_weight_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(h->ada.w32, h->NT, H, h->ada.w16, H);
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+    fmt_destroy(h);
+    return set_err(-2, "fmt_create: weight packing failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+#undef TRY
+  *out = h;
+  return 0;
+}
+
+int32_t fmt_destroy(FmtHandle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  for (void* p : h->owned) cudaFree(p);
+  DevBuf* bufs[] = {&h->cond, &h->cemb, &h->temb, &h->tfreq, &h->th, &h->silu, &h->table, &h->xstate, &h->ystage, &h->kbuf, &h->prevx, &h->ax,
+                    &h->X, &h->A1, &h->QKV, &h->A2, &h->Hm, &h->V, &h->ddt, &h->dteval, &h->wargs, &h->st_rs, &h->st_wa, &h->st_we, &h->st_noise, &h->st_rd};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  delete h;
+  return 0;
+}
+
+int64_t fmt_workspace_bytes(const FmtHandle* h) { return h ? static_cast<int64_t>(h->ws_bytes) : 0; }
+int64_t fmt_launch_count(const FmtHandle* hc, int32_t reset) {
+  FmtHandle* h = const_cast<FmtHandle*>(hc);
+  if (!h) return 0;
+  const long long v = h->launches;
+  if (reset) h->launches = 0;
+  return v;
+}
+int32_t fmt_graph_kernel_nodes(const FmtHandle* h) { return h ? h->graph_nodes : 0; }
+
+static bool same_plan(const FmtHandle* h, const FmtPlan* p) {
+  if (!h->configured) return false;
+  const FmtPlan& q = h->plan;
+  if (q.batch != p->batch || q.n_branches != p->n_branches || q.we_dynamic != p->we_dynamic || q.mode != p->mode ||
+      q.n_steps != p->n_steps || q.n_stages != p->n_stages)
+    return false;
+  const int ne = p->n_steps * p->n_stages;
+  if (ne > 0 && memcmp(h->t_eval.data(), p->t_eval, ne * sizeof(float)) != 0) return false;
+  if (p->n_steps > 0 && memcmp(h->dt.data(), p->dt, p->n_steps * sizeof(float)) != 0) return false;
+  if (memcmp(h->rk_a.data(), p->rk_a, p->n_stages * p->n_stages * sizeof(float)) != 0) return false;
+  if (memcmp(h->rk_b.data(), p->rk_b, p->n_stages * sizeof(float)) != 0) return false;
+  return true;
+}
+
+int32_t fmt_configure(FmtHandle* h, const FmtPlan* p, void* stream) {
+  REQUIRE(h && p, "fmt_configure: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_OK(cudaSetDevice(h->device));
+  REQUIRE(p->batch >= 1, "fmt_configure: batch must be >= 1");
+  REQUIRE(p->n_branches == 1 || p->n_branches == 3 || p->n_branches == 4, "fmt_configure: n_branches must be 1, 3 or 4");
+  REQUIRE(p->mode == FMT_MODE_BF16 || p->mode == FMT_MODE_FP32_VALIDATE, "fmt_configure: unknown mode %d", p->mode);
+  REQUIRE(p->n_steps >= 0 && p->n_stages >= 1 && p->n_stages <= FMT_MAX_STAGES, "fmt_configure: bad n_steps/n_stages");
+  REQUIRE(p->rk_a && p->rk_b && (p->n_steps == 0 || (p->t_eval && p->dt)), "fmt_configure: null schedule arrays");
+  if (same_plan(h, p)) return 0;
+
+  const FmtDims& d = h->d;
+  const int ne = p->n_steps * p->n_stages;
+  h->configured = false;
+  if (h->graph_exec) { CUDA_OK(cudaStreamSynchronize(st)); cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; h->graph_nodes = 0; }
+  h->plan = *p;
+  h->t_eval.assign(p->t_eval, p->t_eval + ne);
+  h->dt.assign(p->dt, p->dt + p->n_steps);
+  h->rk_a.assign(p->rk_a, p->rk_a + p->n_stages * p->n_stages);
+  h->rk_b.assign(p->rk_b, p->rk_b + p->n_stages);
+  h->plan.t_eval = h->plan.dt = h->plan.rk_a = h->plan.rk_b = nullptr;
+  h->n_eval = ne;
+
+  ModelShape& s = h->shape;
+  s.B = p->batch; s.nb = p->n_branches; s.N = h->N; s.P = d.num_prev_frames; s.L = d.frames_per_clip;
+  s.W = d.dim_w; s.A = d.dim_a; s.E = d.dim_e; s.H = d.dim_h; s.Kc = h->Kc; s.we_dynamic = p->we_dynamic;
+  if (s.nb == 3) { s.null_a = 0b001; s.null_r = 0; s.null_e = 0b101; }            // [uncond | all | audio-only]   FMT.py:360-362
+  else if (s.nb == 4) { s.null_a = 0b0011; s.null_r = 0b0001; s.null_e = 0b1011; } // [truly-uncond | uncond | all | audio-only] :382-384
+  else { s.null_a = s.null_r = s.null_e = 0; }
+  h->R = s.nb * s.B * s.N;
+  h->U = h->R;
+  const size_t ts = p->mode == FMT_MODE_BF16 ? 2 : 4;
+  h->tsize = ts;
+  const size_t R = h->R, U = h->U, H = s.H;
+  // table chunking: keep at most ~48 GB of AdaLN tables resident
+  const size_t per_eval = U * static_cast<size_t>(h->NT) * ts;
+  size_t chunk = per_eval ? (static_cast<size_t>(48) << 30) / per_eval : 1;
+  if (chunk < 1) chunk = 1;
+  if (chunk > static_cast<size_t>(ne > 0 ? ne : 1)) chunk = ne > 0 ? ne : 1;
+  h->table_chunk = static_cast<int>(chunk);
+
+  const size_t nx = static_cast<size_t>(s.B) * s.L * s.W;
+  FMT_OK(dev_alloc(h, h->cond, U * s.Kc * ts));
+  FMT_OK(dev_alloc(h, h->cemb, U * H * 4));
+  FMT_OK(dev_alloc(h, h->temb, static_cast<size_t>(ne > 0 ? ne : 1) * H * 4));
+  FMT_OK(dev_alloc(h, h->tfreq, static_cast<size_t>(ne > 0 ? ne : 1) * 256 * 4));
+  FMT_OK(dev_alloc(h, h->th, static_cast<size_t>(ne > 0 ? ne : 1) * H * 4));
+  FMT_OK(dev_alloc(h, h->silu, chunk * U * H * ts));
+  FMT_OK(dev_alloc(h, h->table, chunk * per_eval));
+  FMT_OK(dev_alloc(h, h->xstate, nx * 4));
+  FMT_OK(dev_alloc(h, h->ystage, nx * 4));
+  FMT_OK(dev_alloc(h, h->kbuf, nx * 4 * p->n_stages));
+  FMT_OK(dev_alloc(h, h->prevx, static_cast<size_t>(s.B) * (s.P > 0 ? s.P : 1) * s.W * 4));
+  FMT_OK(dev_alloc(h, h->ax, R * s.W * ts));
+  FMT_OK(dev_alloc(h, h->X, R * H * 4));
+  FMT_OK(dev_alloc(h, h->A1, R * H * ts));
+  FMT_OK(dev_alloc(h, h->QKV, R * 3 * H * ts));
+  FMT_OK(dev_alloc(h, h->A2, R * H * ts));
+  FMT_OK(dev_alloc(h, h->Hm, R * static_cast<size_t>(d.mlp_hidden) * ts));
+  FMT_OK(dev_alloc(h, h->V, R * s.W * 4));
+  FMT_OK(dev_alloc(h, h->ddt, static_cast<size_t>(p->n_steps > 0 ? p->n_steps : 1) * 4));
+  FMT_OK(dev_alloc(h, h->dteval, static_cast<size_t>(ne > 0 ? ne : 1) * 4));
+  FMT_OK(dev_alloc(h, h->wargs, sizeof(WindowArgs)));
+  CUDA_OK(cudaMemsetAsync(h->prevx.p, 0, h->prevx.bytes, st));
+
+  if (ne > 0) {
+    // timestep embeddings of every evaluation (FMT.py:294), computed once per plan
+    CUDA_OK(cudaMemcpyAsync(h->dteval.p, h->t_eval.data(), ne * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(h->ddt.p, h->dt.data(), p->n_steps * sizeof(float), cudaMemcpyHostToDevice, st));
+    timestep_freq_kernel<<<ne, 128, 0, st>>>(static_cast<const float*>(h->dteval.p), ne, static_cast<float*>(h->tfreq.p));
+    LAUNCH_CHECK(); count_launch(h);
+    const int w1 = ne * s.H;
+    small_linear_kernel<<<(w1 * 32 + 255) / 256, 256, 0, st>>>(static_cast<const float*>(h->tfreq.p), h->t0_w, h->t0_b, static_cast<float*>(h->th.p), ne, s.H, 256, 1);
+    LAUNCH_CHECK(); count_launch(h);
+    small_linear_kernel<<<(w1 * 32 + 255) / 256, 256, 0, st>>>(static_cast<const float*>(h->th.p), h->t2_w, h->t2_b, static_cast<float*>(h->temb.p), ne, s.H, s.H, 0);
+    LAUNCH_CHECK(); count_launch(h);
+    CUDA_OK(cudaStreamSynchronize(st));   // t_eval/dt host vectors may be reassigned by the next configure
+  }
+
+  // capture one window as a CUDA graph
+  {
+    cudaGraph_t graph = nullptr;
+    cudaStream_t cs;
+    CUDA_OK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    // make sure the lazily-set function attributes exist before capture (attribute calls are not capturable work but are legal)
+    CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    h->capturing = true; h->capture_launches = 0;
+    int rc = enqueue_window_mode(h, cs);
+    h->capturing = false;
+    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    if (rc != 0) { if (graph) cudaGraphDestroy(graph); cudaStreamDestroy(cs); return rc; }
+    if (ce != cudaSuccess) { cudaStreamDestroy(cs); return set_err(-2, "graph capture failed: %s", cudaGetErrorString(ce)); }
+    size_t n_nodes = 0;
+    cudaGraphGetNodes(graph, nullptr, &n_nodes);
+    h->graph_nodes = static_cast<int>(n_nodes);
+    ce = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    cudaStreamDestroy(cs);
+    if (ce != cudaSuccess) return set_err(-2, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+  }
+  h->configured = true;
+  return 0;
+}
+
+static int set_wargs(FmtHandle* h, const WindowArgs& a, cudaStream_t st) {
+  set_window_args_kernel<<<1, 1, 0, st>>>(static_cast<WindowArgs*>(h->wargs.p), a);
+  LAUNCH_CHECK(); count_launch(h);
+  return 0;
+}
+
+int32_t fmt_sample_clip(FmtHandle* h, const FmtClip* c, void* stream) {
+  REQUIRE(h && c, "fmt_sample_clip: null argument");
+  REQUIRE(h->configured, "fmt_sample_clip: call fmt_configure first");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_OK(cudaSetDevice(h->device));
+  const ModelShape& s = h->shape;
+  REQUIRE(c->r_s && c->wa && c->we && c->r_d, "fmt_sample_clip: null tensor pointer");
+  REQUIRE(c->audio_num_frames >= 1 && c->T_wa >= 1 && c->T_we >= 1, "fmt_sample_clip: empty clip");
+  REQUIRE(s.we_dynamic ? c->T_we > 1 : c->T_we == 1, "fmt_sample_clip: T_we=%d does not match plan.we_dynamic=%d", c->T_we, s.we_dynamic);
+  const int T = c->audio_num_frames;
+  const int n_win = (T + s.L - 1) / s.L;
+  REQUIRE(c->noise != nullptr, "fmt_sample_clip: noise (x0 of every window) is required");
+  // every window must see at least one real wa (and dynamic we) frame; the reference's F.pad(replicate) fails otherwise
+  REQUIRE((n_win - 1) * s.L < c->T_wa, "fmt_sample_clip: wa has %d frames but window %d starts at frame %d", c->T_wa, n_win - 1, (n_win - 1) * s.L);
+  REQUIRE(!s.we_dynamic || (n_win - 1) * s.L < c->T_we, "fmt_sample_clip: dynamic we has %d frames but the last window starts at %d", c->T_we, (n_win - 1) * s.L);
+
+  const float *r_s = c->r_s, *wa = c->wa, *we = c->we, *noise = c->noise;
+  float* r_d = c->r_d;
+  const size_t n_rs = static_cast<size_t>(s.B) * s.W, n_wa = static_cast<size_t>(s.B) * c->T_wa * s.A, n_we = static_cast<size_t>(s.B) * c->T_we * s.E;
+  const size_t n_noise = static_cast<size_t>(n_win) * s.B * s.L * s.W, n_rd = static_cast<size_t>(s.B) * T * s.W;
+  if (c->location == FMT_LOC_HOST) {
+    FMT_OK(dev_alloc(h, h->st_rs, n_rs * 4)); FMT_OK(dev_alloc(h, h->st_wa, n_wa * 4)); FMT_OK(dev_alloc(h, h->st_we, n_we * 4));
+    FMT_OK(dev_alloc(h, h->st_noise, n_noise * 4)); FMT_OK(dev_alloc(h, h->st_rd, n_rd * 4));
+    CUDA_OK(cudaMemcpyAsync(h->st_rs.p, r_s, n_rs * 4, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(h->st_wa.p, wa, n_wa * 4, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(h->st_we.p, we, n_we * 4, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(h->st_noise.p, noise, n_noise * 4, cudaMemcpyHostToDevice, st));
+    r_s = static_cast<float*>(h->st_rs.p); wa = static_cast<float*>(h->st_wa.p); we = static_cast<float*>(h->st_we.p);
+    noise = static_cast<float*>(h->st_noise.p); r_d = static_cast<float*>(h->st_rd.p);
+  }
+  for (int w = 0; w < n_win; ++w) {
+    WindowArgs a{};
+    a.r_s = r_s; a.wa = wa; a.we = we; a.r_d = r_d;
+    a.x0 = noise + static_cast<size_t>(w) * s.B * s.L * s.W;
+    a.T_wa = c->T_wa; a.T_we = c->T_we; a.T_out = T;
+    a.win_start = w * s.L; a.first_window = (w == 0); a.use_ext = 0;
+    a.a_scale = c->a_cfg_scale; a.r_scale = c->r_cfg_scale; a.e_scale = c->e_cfg_scale;
+    FMT_OK(set_wargs(h, a, st));
+    CUDA_OK(cudaGraphLaunch(h->graph_exec, st));
+    h->launches += h->capture_launches;
+    if (c->progress) c->progress(w, n_win, c->progress_user);
+  }
+  if (c->location == FMT_LOC_HOST) {
+    CUDA_OK(cudaMemcpyAsync(c->r_d, r_d, n_rd * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+int32_t fmt_velocity(FmtHandle* h, const FmtEval* ev, void* stream) {
+  REQUIRE(h && ev, "fmt_velocity: null argument");
+  REQUIRE(h->configured, "fmt_velocity: call fmt_configure first");
+  REQUIRE(ev->eval_index >= 0 && ev->eval_index < h->n_eval, "fmt_velocity: eval_index %d out of range [0,%d)", ev->eval_index, h->n_eval);
+  REQUIRE(ev->x && ev->prev_x && ev->wa && ev->prev_wa && ev->we && ev->r_s && ev->v_out, "fmt_velocity: null tensor pointer");
+  REQUIRE(!h->shape.we_dynamic || ev->prev_we, "fmt_velocity: dynamic we requires prev_we (FMT.py:306-307)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_OK(cudaSetDevice(h->device));
+  const ModelShape& s = h->shape;
+  WindowArgs a{};
+  a.r_s = ev->r_s; a.wa = ev->wa; a.we = ev->we; a.x0 = ev->x; a.r_d = nullptr;
+  a.prev_x_ext = ev->prev_x; a.prev_wa_ext = ev->prev_wa; a.prev_we_ext = ev->prev_we;
+  a.T_wa = s.L; a.T_we = s.we_dynamic ? s.L : 1; a.T_out = s.L; a.win_start = 0; a.first_window = 0; a.use_ext = 1;
+  a.a_scale = ev->a_cfg_scale; a.r_scale = ev->r_cfg_scale; a.e_scale = ev->e_cfg_scale;
+  FMT_OK(set_wargs(h, a, st));
+  if (h->plan.mode == FMT_MODE_BF16) {
+    FMT_OK(enqueue_prepare<bf16>(h, st));
+    FMT_OK(enqueue_tables<bf16>(h, ev->eval_index, 1, st));
+    FMT_OK(enqueue_forward<bf16>(h, 0, ev->x, st));
+  } else {
+    FMT_OK(enqueue_prepare<float>(h, st));
+    FMT_OK(enqueue_tables<float>(h, ev->eval_index, 1, st));
+    FMT_OK(enqueue_forward<float>(h, 0, ev->x, st));
+  }
+  FMT_OK(launch_combine(h, 0, ev->v_out, nullptr, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ diagnostics
+static int debug_handle(FmtHandle& h) {
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return set_err(-4, "device is sm_%d%d; sm_100a required", prop.major, prop.minor);
+  h.device = dev; h.num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_OK(cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres));
+  REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+  h.encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  return 0;
+}
+
+int32_t fmt_debug_gemm_bf16(const void* A, const void* W, const float* bias, float* out, int32_t M, int32_t N, int32_t K, int32_t block_n, void* stream) {
+  FmtHandle h;
+  FMT_OK(debug_handle(h));
+  EpiParams ep = epi(EPI_STORE, M, N, bias, out, N, 1);
+  return gemm_bf16(&h, static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), K, ep, K, static_cast<cudaStream_t>(stream), block_n);
+}
+
+int32_t fmt_debug_gemm_fp32(const float* A, const float* W, const float* bias, float* out, int32_t M, int32_t N, int32_t K, void* stream) {
+  FmtHandle h;
+  EpiParams ep = epi(EPI_STORE, M, N, bias, out, N, 1);
+  return gemm_f32(&h, A, K, W, K, ep, K, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,312 @@
+// Non-GEMM kernels of the FMT sampling step.  All are bandwidth-trivial next to the weight stream; they exist to
+// keep the data in the layout / precision the GEMMs want and to fuse what the reference does in separate torch ops.
+//   AT = activation (GEMM operand) type: __nv_bfloat16 (FMT_MODE_BF16) or float (FMT_MODE_FP32_VALIDATE)
+//   TT = AdaLN table type:               __nv_bfloat16                 or float
+// Row layout of every activation matrix: m = branch * (B*N) + b * N + f, N = P + L frames (context first) - the
+// same order the reference's batch-concatenated CFG forward uses (FMT.py:360-372).
+#pragma once
+#include "gemm.cuh"
+
+namespace fmt {
+
+// Per-window arguments, written to device memory by set_window_args so that the captured graph never changes.
+struct WindowArgs {
+  const float* r_s;        // (B, W)
+  const float* wa;         // (B, T_wa, A)
+  const float* we;         // (B, T_we, E)
+  const float* x0;         // (B, L, W) noise of this window (or the explicit x of fmt_velocity)
+  float* r_d;              // (B, T_out, W)
+  const float* prev_x_ext; // explicit context (fmt_velocity) or nullptr = use the chained device state
+  const float* prev_wa_ext;
+  const float* prev_we_ext;
+  int T_wa, T_we, T_out;
+  int win_start;           // first frame of this window in the clip
+  int first_window;        // 1: context is all-zero (nodes_adv.py:591-593)
+  int use_ext;             // 1: prev_* come from the *_ext pointers
+  float a_scale, r_scale, e_scale;
+};
+
+struct ModelShape {
+  int B, nb, N, P, L, W, A, E, H, Kc;   // Kc = padded c_embedder K (multiple of 64)
+  int we_dynamic;
+  unsigned null_a, null_r, null_e;      // bit br set = that condition is zeroed in branch br (FMT.py:360-392)
+};
+
+__global__ void set_window_args_kernel(WindowArgs* dst, WindowArgs v) { *dst = v; }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Condition rows  [wr | wa | we | 0-pad]  for every (branch, clip, frame)   (FMT.py:312-333, nodes_adv.py:609-627,663-686)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename AT>
+__global__ void cond_gather_kernel(const WindowArgs* __restrict__ wargs, ModelShape s, AT* __restrict__ cond) {
+  const WindowArgs a = *wargs;
+  const int rows = s.nb * s.B * s.N;
+  const int row = blockIdx.x;
+  if (row >= rows) return;
+  const int br = row / (s.B * s.N), b = (row / s.N) % s.B, f = row % s.N;
+  const bool za = (s.null_a >> br) & 1, zr = (s.null_r >> br) & 1, ze = (s.null_e >> br) & 1;
+  const bool ctx = f < s.P;
+  // frame of the clip this row looks at; replicate padding == clamp to the last available frame
+  const int g = a.win_start + f - s.P;
+  AT* out = cond + static_cast<size_t>(row) * s.Kc;
+  for (int j = threadIdx.x; j < s.Kc; j += blockDim.x) {
+    float v = 0.f;
+    if (j < s.W) {
+      v = zr ? 0.f : a.r_s[static_cast<size_t>(b) * s.W + j];
+    } else if (j < s.W + s.A) {
+      const int k = j - s.W;
+      if (ctx) {   // prev_wa is replicated un-nulled in every branch (FMT.py:366,388)
+        if (a.use_ext) v = a.prev_wa_ext[(static_cast<size_t>(b) * s.P + f) * s.A + k];
+        else if (!a.first_window) v = a.wa[(static_cast<size_t>(b) * a.T_wa + min(g, a.T_wa - 1)) * s.A + k];
+      } else if (!za) {
+        v = a.wa[(static_cast<size_t>(b) * a.T_wa + min(g, a.T_wa - 1)) * s.A + k];
+      }
+    } else if (j < s.W + s.A + s.E) {
+      const int k = j - s.W - s.A;
+      if (!ze) {
+        if (!s.we_dynamic) {
+          v = a.we[static_cast<size_t>(b) * s.E + k];     // static emotion covers the context frames too (FMT.py:325-326)
+        } else if (ctx) {
+          if (a.use_ext) v = a.prev_we_ext[(static_cast<size_t>(b) * s.P + f) * s.E + k];
+          else if (!a.first_window) v = a.we[(static_cast<size_t>(b) * a.T_we + min(g, a.T_we - 1)) * s.E + k];
+        } else {
+          v = a.we[(static_cast<size_t>(b) * a.T_we + min(g, a.T_we - 1)) * s.E + k];
+        }
+      }
+    }
+    out[j] = from_f32<AT>(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Timestep embedding (FMT.py:107-131), fp32 in every mode.  Runs once per plan.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void timestep_freq_kernel(const float* __restrict__ t, int n_eval, float* __restrict__ emb /* (n_eval, 256) */) {
+  const int e = blockIdx.x, k = threadIdx.x;     // 128 threads
+  const float neg_log = -9.210340371976184f;     // -ln(10000)
+  const float freq = expf(neg_log * static_cast<float>(k) / 128.0f);
+  const float arg = t[e] * freq;
+  emb[e * 256 + k] = cosf(arg);
+  emb[e * 256 + 128 + k] = sinf(arg);
+}
+// out[e, n] = act(sum_k W[n,k] * in[e,k] + b[n]); one warp per output element.
+__global__ void small_linear_kernel(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ b,
+                                    float* __restrict__ out, int n_rows, int N, int K, int silu) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_rows * N) return;
+  const int e = warp / N, n = warp % N;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(W[static_cast<size_t>(n) * K + k], in[static_cast<size_t>(e) * K + k], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    acc += b[n];
+    out[static_cast<size_t>(e) * N + n] = silu ? acc / (1.f + expf(-acc)) : acc;
+  }
+}
+
+// silu_c[(e*U + u), h] = SiLU(c_emb[u, h] + t_emb[e0 + e, h])      (FMT.py:335 then adaLN_modulation[0], :163-166)
+template <typename AT>
+__global__ void silu_cond_kernel(const float* __restrict__ c_emb, const float* __restrict__ t_emb, int e0, int U, int H,
+                                 AT* __restrict__ out, size_t total) {
+  size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= total) return;
+  const int h = static_cast<int>(i % H);
+  const size_t row = i / H;
+  const int u = static_cast<int>(row % U), e = static_cast<int>(row / U);
+  const float4 c = *reinterpret_cast<const float4*>(c_emb + static_cast<size_t>(u) * H + h);
+  const float4 t = *reinterpret_cast<const float4*>(t_emb + static_cast<size_t>(e0 + e) * H + h);
+  float v[4] = {c.x + t.x, c.y + t.y, c.z + t.z, c.w + t.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = v[k] / (1.f + expf(-v[k]));
+  VecIO<AT, 4>::store(out + i, v);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// x-embedder input: rows [prev_x | y] replicated over the CFG branches (FMT.py:312,363-365)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename AT>
+__global__ void pack_x_kernel(const WindowArgs* __restrict__ wargs, ModelShape s, const float* __restrict__ y /* (B,L,W) */,
+                              const float* __restrict__ prev_x_state /* (B,P,W) */, AT* __restrict__ ax) {
+  const WindowArgs a = *wargs;
+  const int row = blockIdx.x;   // b*N + f
+  const int b = row / s.N, f = row % s.N;
+  const float* src;
+  if (f < s.P) src = a.use_ext ? a.prev_x_ext + (static_cast<size_t>(b) * s.P + f) * s.W : prev_x_state + (static_cast<size_t>(b) * s.P + f) * s.W;
+  else src = y + (static_cast<size_t>(b) * s.L + (f - s.P)) * s.W;
+  for (int j = threadIdx.x * 4; j < s.W; j += blockDim.x * 4) {
+    const float4 t = *reinterpret_cast<const float4*>(src + j);
+    float v[4] = {t.x, t.y, t.z, t.w};
+    for (int br = 0; br < s.nb; ++br) VecIO<AT, 4>::store(ax + (static_cast<size_t>(br) * s.B * s.N + row) * s.W + j, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm (eps 1e-6, no affine) + framewise modulate  x*(1+scale)+shift   (FMT.py:157,168-169,174-175,197)
+// One warp per row; statistics in fp32 (two-pass).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename AT, typename TT>
+__global__ void lnmod_kernel(const float* __restrict__ X, int rows, int H, const TT* __restrict__ table, const int* __restrict__ urow,
+                             long long ldt, long long shift_off, long long scale_off, AT* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* x = X + static_cast<size_t>(row) * H;
+  float sum = 0.f;
+  for (int j = lane * 4; j < H; j += 128) {
+    const float4 t = *reinterpret_cast<const float4*>(x + j);
+    sum += (t.x + t.y) + (t.z + t.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / static_cast<float>(H);
+  float var = 0.f;
+  for (int j = lane * 4; j < H; j += 128) {
+    const float4 t = *reinterpret_cast<const float4*>(x + j);
+    const float d0 = t.x - mean, d1 = t.y - mean, d2 = t.z - mean, d3 = t.w - mean;
+    var += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / static_cast<float>(H) + 1e-6f);
+  const TT* trow = table + static_cast<size_t>(urow ? urow[row] : row) * ldt;
+  for (int j = lane * 4; j < H; j += 128) {
+    const float4 t = *reinterpret_cast<const float4*>(x + j);
+    float sh[4], sc[4];
+    VecIO<TT, 4>::load(trow + shift_off + j, sh);
+    VecIO<TT, 4>::load(trow + scale_off + j, sc);
+    float v[4] = {(t.x - mean) * rstd, (t.y - mean) * rstd, (t.z - mean) * rstd, (t.w - mean) * rstd};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = fmaf(v[k], 1.f + sc[k], sh[k]);
+    VecIO<AT, 4>::store(out + static_cast<size_t>(row) * H + j, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Band-masked self-attention (FMT.py:15-19,69-88): row i attends j in [max(0,i-w), min(N-1,i+w)], scale hd^-1/2.
+// One warp per (sequence, head, query row); the <= 2w+1 scores live in registers of the whole warp
+// (dot products reduced with warp shuffles, softmax in fp32).  qkv columns: [q | k | v], each head-major.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename AT, int VPL /* head_dim / 32 */>
+__global__ void band_attention_kernel(const AT* __restrict__ qkv, int n_seq, int N, int heads, int window, float scale,
+                                      AT* __restrict__ out) {
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (gw >= n_seq * heads * N) return;
+  const int i = gw % N, h = (gw / N) % heads, sq = gw / (N * heads);
+  const int hd = VPL * 32, Hd = heads * hd, ld = 3 * Hd;
+  const AT* base = qkv + static_cast<size_t>(sq) * N * ld;
+  float q[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) q[k] = to_f32<AT>(base[static_cast<size_t>(i) * ld + h * hd + lane * VPL + k]) * scale;
+  const int j0 = max(0, i - window), j1 = min(N - 1, i + window);
+  float mx = -INFINITY, den = 0.f, acc[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) acc[k] = 0.f;
+  for (int j = j0; j <= j1; ++j) {        // online softmax over the band
+    const AT* kr = base + static_cast<size_t>(j) * ld + Hd + h * hd + lane * VPL;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) s = fmaf(q[k], to_f32<AT>(kr[k]), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float nmx = fmaxf(mx, s);
+    const float corr = expf(mx - nmx), p = expf(s - nmx);
+    den = den * corr + p;
+    const AT* vr = kr + Hd;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) acc[k] = fmaf(acc[k], corr, p * to_f32<AT>(vr[k]));
+    mx = nmx;
+  }
+  const float inv = 1.f / den;
+  AT* o = out + (static_cast<size_t>(sq) * N + i) * Hd + h * hd + lane * VPL;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) o[k] = from_f32<AT>(acc[k] * inv);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Classifier-free-guidance combine (FMT.py:375-379,396-399), incremental form exactly as the reference writes it.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cfg_combine(const float* __restrict__ V, size_t idx, size_t branch_stride, int nb, float a, float r,
+                                             float e) {
+  if (nb == 1) return V[idx];
+  if (nb == 3) {
+    const float u = V[idx], c = V[idx + branch_stride], ao = V[idx + 2 * branch_stride];
+    return u + a * (ao - u) + e * (c - ao);
+  }
+  const float tu = V[idx], u = V[idx + branch_stride], c = V[idx + 2 * branch_stride], ao = V[idx + 3 * branch_stride];
+  return tu + r * (u - tu) + a * (ao - u) + e * (c - ao);
+}
+
+// mode 0: v_full[b, f, :] = combined, all N frames (fmt_velocity)
+// mode 1: k_out[b, f-P, :] = combined, current frames only (RK stage derivative)
+// mode 2: y[b, f-P, :] += dt * combined   (fused Euler update, torchdiffeq euler: y1 = y0 + dt*f(t0,y0))
+__global__ void cfg_combine_kernel(const WindowArgs* __restrict__ wargs, ModelShape s, const float* __restrict__ V, int mode,
+                                   float* __restrict__ dst, const float* __restrict__ dt_ptr) {
+  const WindowArgs a = *wargs;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t per_branch = static_cast<size_t>(s.B) * s.N * s.W;
+  if (i >= per_branch) return;
+  const int j = static_cast<int>(i % s.W);
+  const int f = static_cast<int>((i / s.W) % s.N), b = static_cast<int>(i / (static_cast<size_t>(s.W) * s.N));
+  if (mode != 0 && f < s.P) return;
+  const float v = cfg_combine(V, i, per_branch, s.nb, a.a_scale, a.r_scale, a.e_scale);
+  if (mode == 0) dst[i] = v;
+  else {
+    const size_t o = (static_cast<size_t>(b) * s.L + (f - s.P)) * s.W + j;
+    if (mode == 1) dst[o] = v;
+    else dst[o] = fmaf(*dt_ptr, v, dst[o]);
+  }
+}
+
+// y_out = y0 + dt * sum_j coef[j] * k_j   (explicit Runge-Kutta stage / final combination)
+__global__ void rk_combine_kernel(const float* __restrict__ y0, float* __restrict__ y_out, const float* __restrict__ k, size_t n,
+                                  size_t k_stride, int n_k, float c0, float c1, float c2, float c3, const float* __restrict__ dt_ptr) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float c[4] = {c0, c1, c2, c3};
+  float acc = 0.f;
+  for (int j = 0; j < n_k; ++j)
+    if (c[j] != 0.f) acc = fmaf(c[j], k[j * k_stride + i], acc);
+  y_out[i] = fmaf(*dt_ptr, acc, y0[i]);
+}
+
+// Window prologue / epilogue: x_state <- x0 ; r_d[:, win] <- x_state, prev_x <- last P frames (nodes_adv.py:659-668,690-692)
+__global__ void init_window_kernel(const WindowArgs* __restrict__ wargs, float* __restrict__ x_state, size_t n,
+                                   float* __restrict__ prev_x_state, size_t n_prev) {
+  const WindowArgs a = *wargs;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) x_state[i] = a.x0[i];
+  if (a.first_window && i < n_prev) prev_x_state[i] = 0.f;
+}
+__global__ void finalize_window_kernel(const WindowArgs* __restrict__ wargs, ModelShape s, const float* __restrict__ x_state,
+                                       float* __restrict__ prev_x_state) {
+  const WindowArgs a = *wargs;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(s.B) * s.L * s.W) return;
+  const int j = static_cast<int>(i % s.W), f = static_cast<int>((i / s.W) % s.L), b = static_cast<int>(i / (static_cast<size_t>(s.W) * s.L));
+  const float v = x_state[i];
+  const int g = a.win_start + f;
+  if (a.r_d != nullptr && g < a.T_out) a.r_d[(static_cast<size_t>(b) * a.T_out + g) * s.W + j] = v;
+  if (f >= s.L - s.P) prev_x_state[(static_cast<size_t>(b) * s.P + (f - (s.L - s.P))) * s.W + j] = v;
+}
+
+// fp32 -> bf16 weight packing (with optional K padding)
+__global__ void pack_weight_kernel(const float* __restrict__ src, int rows, int K, __nv_bfloat16* __restrict__ dst, int Kpad) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(rows) * Kpad) return;
+  const int k = static_cast<int>(i % Kpad);
+  const size_t r = i / Kpad;
+  dst[i] = __float2bfloat16_rn(k < K ? src[r * K + k] : 0.f);
+}
+__global__ void pad_weight_f32_kernel(const float* __restrict__ src, int rows, int K, float* __restrict__ dst, int Kpad) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(rows) * Kpad) return;
+  const int k = static_cast<int>(i % Kpad);
+  const size_t r = i / Kpad;
+  dst[i] = k < K ? src[r * K + k] : 0.f;
+}
+
+}  // namespace fmt
