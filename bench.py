@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the FMT motion-latent sampling path (BASELINE.json metric: motion-latent frames/s, FMT, nfe=10).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--frames T]
+
+One "step" = one sampler call (= ``_perform_ode_sampling_loop``) over one batch of synthetic clips:
+``ceil(T/50)`` windows x ``nfe-1`` Euler steps x 3-way CFG.  Default workload = BASELINE.json configs[1]:
+1 clip, 4 s -> 100 frames, nfe=10, a_cfg=2, e_cfg=1, bf16.  ``--batch 32 --frames 200`` gives the tensor-pipe
+regime of configs[3] (per GPU).  For N > 1 (torchrun) every rank samples its own clips (data parallel, weak
+scaling) and the step ends with one NCCL all-gather of the motion latents.
+
+Prints ONE JSON line (rank 0).  ``value`` = frames/s with inputs resident in HBM, timed with CUDA events, max over
+ranks; ``e2e`` = the same through the node class with CPU tensors in / CPU tensor out (H2D, noise draw, D2H inside
+the timed region); ``roofline`` = algorithmic bytes (or FLOPs) of one window launch / its measured duration against
+MEASURED_PEAKS.json; ``cpu_baseline`` = the oracle port (reference algorithm, torch fp32) on the host cores.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NFE, A_CFG, E_CFG, R_CFG = 10, 2.0, 1.0, 1.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def algorithmic_work(dims, B, nb, S):
+    """Per-window algorithmic bytes / FLOPs, bf16 weights, AdaLN tables hoisted."""
+    H, W, M, D, N = dims.dim_h, dims.dim_w, dims.mlp_hidden, dims.fmt_depth, dims.total_frames
+    Kc = dims.dim_w + dims.dim_a + dims.dim_e
+    NT = D * 6 * H + 2 * H
+    step_params = D * (3 * H * H + H * H + 2 * H * M) + H * W + W * H          # qkv, proj, fc1, fc2, x_embedder, decoder.linear
+    rows = nb * B * N
+    table_bytes = rows * NT * 2                                                 # bf16 shift/scale/gate rows of one evaluation
+    step_bytes = 2 * step_params + table_bytes
+    prep_bytes = 2 * (NT * H + H * Kc) + S * table_bytes                        # adaLN + c_embedder weights once, table written once
+    macs_row = step_params + NT * H + H * Kc                                    # every Linear, per token row (hoisting moves, not removes)
+    attn_flops_row = 4 * N * H                                                  # dense-equivalent QK^T + PV, as the reference computes
+    flops_step = rows * (2 * macs_row + attn_flops_row)
+    return dict(step_bytes=step_bytes, window_bytes=S * step_bytes + prep_bytes, window_flops=S * flops_step, rows=rows)
+
+
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(gpu_index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+        out["reasons"], out["samples"] = sorted(reasons), len(sm)
+        return out
+
+
+def workload_inputs(dims, B, T, rank):
+    from oracle.synth import synth_inputs
+    return synth_inputs(dims, B, T, seed=7 + 1000 * rank)
+
+
+def cpu_reference_clip(W, dims, r_s, wa, we, T, noise):
+    """The reference algorithm on the host cores: oracle/fmt_oracle.py (restatement pinned to the reference's fixtures)."""
+    from oracle import fmt_oracle as O
+    with torch.no_grad():
+        return O.sample_loop(W, dims, r_s, wa, we, T, nfe=NFE, a_cfg_scale=A_CFG, r_cfg_scale=R_CFG, e_cfg_scale=E_CFG, noise=noise)
+
+
+def time_cpu_baseline(W, dims, B, T, budget_s, reps=3):
+    torch.set_num_threads(os.cpu_count() or 1)
+    r_s, wa, we = workload_inputs(dims, B, T, 0)
+    L = dims.frames_per_clip
+    g = torch.Generator().manual_seed(15)
+    n_win = math.ceil(T / L)
+    noise = torch.stack([torch.randn(B, L, dims.dim_w, generator=g) for _ in range(n_win)])
+    # bounded sample: the whole clip if one pass fits the budget, else its first window
+    t0 = time.perf_counter()
+    cpu_reference_clip(W, dims, r_s, wa[:, :L], we[:, :L] if we.shape[1] > 1 else we, L, noise[:1])
+    t_win = time.perf_counter() - t0
+    frames, sample = (T, f"whole workload: {B} clip(s) x {T} frames, {n_win} windows x {NFE - 1} steps, 3-way CFG") \
+        if t_win * n_win * (reps + 0.5) <= budget_s else (L, f"first window only: {B} clip(s) x {L} frames, {NFE - 1} steps, 3-way CFG")
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_reference_clip(W, dims, r_s, wa[:, :frames], we[:, :frames] if we.shape[1] > 1 else we, frames, noise[:math.ceil(frames / L)])
+        best = min(best, time.perf_counter() - t0)
+        if best * reps > budget_s:
+            break
+    return dict(value=B * frames / best, unit="frames/s", cores=torch.get_num_threads(), kind="port", sample=sample,
+                ms_per_ode_step=1e3 * best / (math.ceil(frames / L) * (NFE - 1)))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="clips per GPU")
+    ap.add_argument("--frames", type=int, default=100, help="frames per clip (25 fps)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from oracle.synth import FmtDims, synth_state_dict
+    dims = FmtDims()
+    B, T = args.batch, args.frames
+    L = dims.frames_per_clip
+    n_win = math.ceil(T / L)
+    S = NFE - 1
+    workload = (f"configs[1]: {B} clip x {T} frames (4 s @25 fps), nfe={NFE}, a_cfg={A_CFG}, e_cfg={E_CFG}, 3-way CFG, euler, bf16"
+                if (B, T) == (1, 100) else f"{B} clips/GPU x {T} frames, nfe={NFE}, a_cfg={A_CFG}, e_cfg={E_CFG}, 3-way CFG, euler, bf16")
+    config = dict(workload=workload, clips_per_gpu=B, frames_per_clip=T, windows=n_win, ode_steps_per_window=S, cfg_branches=3,
+                  parallelism=f"dp{world}", l2="256 MiB memset between timed iterations (L2 flush)")
+
+    # ------------------------------------------------------------------ reference arm: the CPU port, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        W = synth_state_dict(dims, seed=0)
+        torch.set_num_threads(os.cpu_count() or 1)
+        r_s, wa, we = workload_inputs(dims, B, T, 0)
+        g = torch.Generator().manual_seed(15)
+        noise = torch.stack([torch.randn(B, L, dims.dim_w, generator=g) for _ in range(n_win)])
+        t0 = time.perf_counter()
+        cpu_reference_clip(W, dims, r_s, wa[:, :L], we, L, noise[:1])
+        t_win = time.perf_counter() - t0
+        total = args.steps + args.warmup
+        frames = T if t_win * n_win * total <= 150 else L
+        sample = (f"whole workload per step ({B} clip x {T} frames)" if frames == T else
+                  f"first window per step ({B} clip x {L} frames, {S} ODE steps)") + "; oracle port of the reference (torch fp32, CPU)"
+        nw = math.ceil(frames / L)
+        for _ in range(max(0, args.warmup - 1)):
+            cpu_reference_clip(W, dims, r_s, wa[:, :frames], we, frames, noise[:nw])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_reference_clip(W, dims, r_s, wa[:, :frames], we, frames, noise[:nw])
+        el = time.perf_counter() - t0
+        v = args.steps * B * frames / el
+        print(json.dumps(dict(impl="reference", metric="motion-latent frames/s (FMT, nfe=10)", value=v, unit="frames/s", n_gpus=args.gpus,
+                              steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * el / args.steps, higher_is_better=True, scaling="weak",
+                              vs_baseline=None, dtype="f32", data="synthetic", config=config,
+                              cpu_baseline=dict(value=v, unit="frames/s", cores=torch.get_num_threads(), kind="port", sample=sample),
+                              e2e=dict(value=v, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    W = synth_state_dict(dims, seed=0)
+    model = pkg.FmtModel(W, target_device=dev)
+    be = pkg.backend_for(model, dev)
+    be.configure(B, 3, False, NFE, "euler", "bf16")
+    r_s, wa, we = workload_inputs(dims, B, T, rank)
+    r_s_d, wa_d, we_d = r_s.to(dev), wa.to(dev), we.to(dev)
+    g = torch.Generator(dev).manual_seed(15 + rank)
+    noise_d = pkg.draw_window_noise(B, be.dims, n_win, dev, g)
+    out_d = torch.empty(B, T, dims.dim_w, device=dev)
+    gathered = torch.empty(world * B, T, dims.dim_w, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_resident():
+        be.sample_clip(r_s_d, wa_d, we_d, T, noise_d, A_CFG, R_CFG, E_CFG, out=out_d)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out_d)        # the only collective of the path: final gather of r_d
+
+    node = pkg.FloatSampleMotionSequenceRD_VA()
+    r_s_p, wa_p, we_p = r_s.pin_memory(), wa.pin_memory(), we.pin_memory()
+
+    def step_e2e():
+        out, _ = node.sample_rd_sequence_va(r_s_p, wa_p, we_p, T, model, A_CFG, R_CFG, E_CFG, False, NFE, "euler", 1e-5, 1e-5,
+                                            0.1, 0.1, 0.1, True, 15 + rank)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n, wall=False):
+        """n iterations; device time from CUDA event pairs around each iteration (L2 flushed outside the pairs)."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        barrier()
+        t_wall = 0.0
+        for e0, e1 in evs:
+            flush.zero_()
+            if wall:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            e0.record()
+            fn()
+            e1.record()
+            if wall:
+                torch.cuda.synchronize()
+                t_wall += time.perf_counter() - t0
+        barrier()
+        t_dev = sum(e0.elapsed_time(e1) for e0, e1 in evs) * 1e-3
+        t = torch.tensor([t_wall if wall else t_dev], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    be.launch_count(reset=True)
+    t_res = timed(step_resident, args.steps)
+    launches = be.launch_count(reset=True)
+    for _ in range(3):
+        step_e2e()
+    n_e2e = max(10, args.steps // 4)
+    t_e2e = timed(step_e2e, n_e2e, wall=True)        # host-visible latency: the call returns a CPU tensor
+    clk = clocks.stop() if clocks else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    work = algorithmic_work(dims, B, 3, S)
+    t_step = t_res / args.steps
+    t_window = t_step / n_win
+    frames_total = world * B * T
+    hbm_achieved = work["window_bytes"] / t_window / 1e9
+    tf_achieved = work["window_flops"] / t_window / 1e12
+    hbm_frac, tf_frac = hbm_achieved / pk["hbm_gbs"], tf_achieved / pk["bf16_tflops_sustained"]
+    if hbm_frac >= tf_frac:
+        roof = dict(bound="hbm", achieved=hbm_achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=hbm_frac, traffic=None)
+    else:
+        roof = dict(bound="tensor", achieved=tf_achieved, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s", frac=tf_frac, traffic=None)
+    roof.update(peak_source=pk["source"], launch="one captured window graph = prepare + %d ODE steps" % S,
+                us_per_ode_step=1e6 * t_window / S, algorithmic_bytes_per_window=work["window_bytes"],
+                algorithmic_flops_per_window=work["window_flops"], other_bound_frac=min(hbm_frac, tf_frac))
+    h2d = (r_s.numel() + wa.numel() + we.numel()) * 4
+    d2h = B * T * dims.dim_w * 4
+    res = dict(metric="motion-latent frames/s (FMT, nfe=10)", value=frames_total / t_step, unit="frames/s", n_gpus=world, steps=args.steps,
+               warmup=max(3, args.warmup), ms_per_step=1e3 * t_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+               data="synthetic", config=config, us_per_ode_step=1e6 * t_window / S,
+               e2e=dict(value=frames_total / (t_e2e / n_e2e), unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                        ms_per_step=1e3 * t_e2e / n_e2e, api="FloatSampleMotionSequenceRD_VA.sample_rd_sequence_va (CPU tensors in/out)"),
+               gpu_launches=int(launches), graph_kernel_nodes=be.graph_kernel_nodes(), roofline=roof, clocks=clk)
+    if not args.no_cpu_baseline and world == 1:
+        res["cpu_baseline"] = time_cpu_baseline(W, dims, B, T, budget_s=25.0)
+    print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
