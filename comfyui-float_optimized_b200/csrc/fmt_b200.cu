@@ -5,11 +5,15 @@
 // which runs entirely on the device: windows are chained through prev_x / prev_wa / prev_we without host syncs.
 #include "../../include/fmt_b200.h"
 #include "kernels.cuh"
+#include "skinny.cuh"
+
+#include <cstdlib>
 
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 using namespace fmt;
@@ -79,6 +83,11 @@ struct FmtHandle {
   // workspace
   DevBuf cond, cemb, temb, tfreq, th, silu, table, xstate, ystage, kbuf, prevx, ax, X, A1, QKV, A2, Hm, V, ddt, dteval, wargs;
   DevBuf st_rs, st_wa, st_we, st_noise, st_rd;   // staging for host-located clips
+  DevBuf sk_scratch, sk_counters;                // split-K fix-up state of the skinny GEMM (kept all-zero between launches)
+  bool use_pdl = true;                           // programmatic dependent launch between graph nodes (FMT_PDL=0 disables)
+  bool use_skinny = true;                        // skinny-M GEMM for M <= 256 (FMT_SKINNY=0 disables)
+  int sk_cluster = 8;                            // cluster size of the skinny GEMM (FMT_SK_CLUSTER)
+  int sk_target_ctas = 128;                      // K-split until about this many CTAs (FMT_SK_CTAS)
   size_t ws_bytes = 0;
 
   cudaGraphExec_t graph_exec = nullptr;
@@ -109,6 +118,30 @@ static inline void count_launch(FmtHandle* h) {
 }
 #define LAUNCH_CHECK() CUDA_OK(cudaGetLastError())
 
+// All kernels of the step go through here: optional thread-block cluster + programmatic dependent launch, so that in the
+// captured graph the prologue (barrier init, TMEM alloc, weight prefetch) of node i+1 overlaps the tail of node i.
+template <typename... KArgs, typename... Args>
+static int launch(FmtHandle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  if (cluster > 1) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = cluster; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (h->use_pdl) {
+    attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attrs; cfg.numAttrs = na;
+  CUDA_OK(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
+  count_launch(h);
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ GEMM launch
 static int make_tmap(FmtHandle* h, CUtensorMap* m, const void* ptr, int rows, int cols, int ld_elems, int box_rows) {
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
@@ -135,10 +168,44 @@ static int launch_tc(FmtHandle* h, const bf16* A, int lda, const bf16* W, int ld
   FMT_OK(make_tmap(h, &tb, W, ep.N, K, ldw, BN));
   const int tiles = ((ep.M + C::BM - 1) / C::BM) * ((ep.N + BN - 1) / BN);
   const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-  gemm_tc_kernel<BN, bf16><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, ep, K);
-  LAUNCH_CHECK();
-  count_launch(h);
-  return 0;
+  return launch(h, gemm_tc_kernel<BN, bf16>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, 1, ta, tb, ep, K);
+}
+
+// ---- skinny-M path (weights as the UMMA M operand, all rows as N; see skinny.cuh)
+static int make_tmap_box(FmtHandle* h, CUtensorMap* m, const void* ptr, int rows, int cols, int ld_elems, int box_rows);
+
+static int gemm_skinny(FmtHandle* h, const bf16* A, int lda, const bf16* W, int ldw, const EpiParams& ep, int K, cudaStream_t st) {
+  static bool attr_set[64] = {};
+  int CL = h->sk_cluster;
+  const int n_ft = ep.N / 128;
+  while (CL > 1 && n_ft % CL != 0) CL >>= 1;
+  const int align = 8 * CL > 16 ? 8 * CL : 16;
+  int Mpad = ((ep.M + align - 1) / align) * align;
+  while (Mpad > 256 && CL > 1) { CL >>= 1; const int al = 8 * CL > 16 ? 8 * CL : 16; Mpad = ((ep.M + al - 1) / al) * al; }
+  REQUIRE(Mpad <= 256, "gemm_skinny: M=%d too large", ep.M);
+  const int nkb = K / 64;
+  // K-split: largest divisor of nkb that keeps the grid at or below the CTA target
+  int n_ks = 1;
+  for (int d = 1; d <= nkb; ++d)
+    if (nkb % d == 0 && n_ft * d <= h->sk_target_ctas) n_ks = d;
+  SkinnyParams sp{};
+  sp.ep = ep; sp.K = K; sp.Mpad = Mpad; sp.n_ft = n_ft; sp.n_ks = n_ks; sp.kb_per_split = nkb / n_ks;
+  sp.scratch = static_cast<float*>(h->sk_scratch.p); sp.counters = static_cast<int*>(h->sk_counters.p);
+  if (n_ks > 1 && ep.kind != EPI_GATE_RES)
+    REQUIRE(static_cast<size_t>(ep.M) * ep.N * 4 <= h->sk_scratch.bytes && static_cast<size_t>(n_ft) * 4 <= h->sk_counters.bytes,
+            "gemm_skinny: split-K scratch too small");
+  const int smem = sk_smem_bytes(Mpad);
+  if (!attr_set[h->device & 63]) {
+    CUDA_OK(cudaFuncSetAttribute(skinny_gemm_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem_bytes(256)));
+    attr_set[h->device & 63] = true;
+  }
+  CUtensorMap tw, ta;
+  FMT_OK(make_tmap_box(h, &tw, W, ep.N, K, ldw, 128));
+  FMT_OK(make_tmap_box(h, &ta, A, ep.M, K, lda, Mpad / CL));
+  return launch(h, skinny_gemm_kernel<bf16>, dim3(n_ft * n_ks), dim3(SK_THREADS), smem, st, CL, tw, ta, sp);
+}
+static int make_tmap_box(FmtHandle* h, CUtensorMap* m, const void* ptr, int rows, int cols, int ld_elems, int box_rows) {
+  return make_tmap(h, m, ptr, rows, cols, ld_elems, box_rows);
 }
 
 static int pick_bn(const FmtHandle* h, int M, int N) {
@@ -150,7 +217,9 @@ static int pick_bn(const FmtHandle* h, int M, int N) {
 
 static int gemm_bf16(FmtHandle* h, const bf16* A, int lda, const bf16* W, int ldw, const EpiParams& ep, int K, cudaStream_t st, int force_bn = 0) {
   REQUIRE(ep.N % 32 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm_bf16: N %% 32, K/lda/ldw %% 8 required (N=%d K=%d)", ep.N, K);
-  const int bn = force_bn ? force_bn : pick_bn(h, ep.M, ep.N);
+  if (force_bn == -1 || (force_bn == 0 && h->use_skinny && ep.M <= 256 && ep.N % 128 == 0 && K % 64 == 0 && h->sk_scratch.p != nullptr))
+    return gemm_skinny(h, A, lda, W, ldw, ep, K, st);
+  const int bn = force_bn > 0 ? force_bn : pick_bn(h, ep.M, ep.N);
   switch (bn) {
     case 256: return launch_tc<256>(h, A, lda, W, ldw, ep, K, st);
     case 128: return launch_tc<128>(h, A, lda, W, ldw, ep, K, st);
@@ -162,10 +231,7 @@ static int gemm_bf16(FmtHandle* h, const bf16* A, int lda, const bf16* W, int ld
 static int gemm_f32(FmtHandle* h, const float* A, int lda, const float* W, int ldw, const EpiParams& ep, int K, cudaStream_t st) {
   REQUIRE(ep.N % 4 == 0 && K % 16 == 0 && lda % 4 == 0 && ldw % 4 == 0, "gemm_f32: N %% 4, K %% 16 required (N=%d K=%d)", ep.N, K);
   dim3 grid((ep.N + 63) / 64, (ep.M + 63) / 64);
-  gemm_simt_kernel<<<grid, 256, 0, st>>>(A, lda, W, ldw, ep, K);
-  LAUNCH_CHECK();
-  count_launch(h);
-  return 0;
+  return launch(h, gemm_simt_kernel, grid, dim3(256), 0, st, 1, A, lda, W, ldw, ep, K);
 }
 
 template <typename T> struct ModeOps;
@@ -191,8 +257,7 @@ template <typename T>
 static int enqueue_prepare(FmtHandle* h, cudaStream_t st) {
   const ModelShape& s = h->shape;
   const WindowArgs* wa = static_cast<const WindowArgs*>(h->wargs.p);
-  cond_gather_kernel<T><<<h->U, 128, 0, st>>>(wa, s, static_cast<T*>(h->cond.p));
-  LAUNCH_CHECK(); count_launch(h);
+  FMT_OK(launch(h, cond_gather_kernel<T>, dim3(h->U), dim3(128), 0, st, 1, wa, s, static_cast<T*>(h->cond.p)));
   EpiParams ep = epi(EPI_STORE, h->U, s.H, h->c_emb.b, h->cemb.p, s.H, 1);
   FMT_OK(ModeOps<T>::gemm(h, h->cond.p, s.Kc, h->c_emb, ep, st));
   return 0;
@@ -203,9 +268,8 @@ template <typename T>
 static int enqueue_tables(FmtHandle* h, int e0, int n, cudaStream_t st) {
   const ModelShape& s = h->shape;
   const size_t total = static_cast<size_t>(n) * h->U * s.H;
-  silu_cond_kernel<T><<<static_cast<unsigned>((total / 4 + 255) / 256), 256, 0, st>>>(
-      static_cast<const float*>(h->cemb.p), static_cast<const float*>(h->temb.p), e0, h->U, s.H, static_cast<T*>(h->silu.p), total);
-  LAUNCH_CHECK(); count_launch(h);
+  FMT_OK(launch(h, silu_cond_kernel<T>, dim3(static_cast<unsigned>((total / 4 + 255) / 256)), dim3(256), 0, st, 1,
+                static_cast<const float*>(h->cemb.p), static_cast<const float*>(h->temb.p), e0, h->U, s.H, static_cast<T*>(h->silu.p), total));
   EpiParams ep = epi(EPI_STORE, n * h->U, h->NT, h->ada.b, h->table.p, h->NT, 0);
   FMT_OK(ModeOps<T>::gemm(h, h->silu.p, s.H, h->ada, ep, st));
   return 0;
@@ -214,43 +278,47 @@ static int enqueue_tables(FmtHandle* h, int e0, int n, cudaStream_t st) {
 template <typename T>
 static int launch_lnmod(FmtHandle* h, const T* table_e, long long shift_off, long long scale_off, cudaStream_t st) {
   const ModelShape& s = h->shape;
-  const int warps = 8;
-  lnmod_kernel<T, T><<<(h->R + warps - 1) / warps, warps * 32, 0, st>>>(static_cast<const float*>(h->X.p), h->R, s.H, table_e, nullptr,
-                                                                        h->NT, shift_off, scale_off, static_cast<T*>(h->A1.p));
-  LAUNCH_CHECK(); count_launch(h);
-  return 0;
+  const int warps = 4;
+  const dim3 grid((h->R + warps - 1) / warps), block(warps * 32);
+  const float* X = static_cast<const float*>(h->X.p);
+  T* out = static_cast<T*>(h->A1.p);
+  const int* urow = nullptr;
+  const long long ldt = h->NT;
+  switch (s.H / 128) {
+    case 1: return launch(h, lnmod_kernel<T, T, 1>, grid, block, 0, st, 1, X, h->R, s.H, table_e, urow, ldt, shift_off, scale_off, out);
+    case 2: return launch(h, lnmod_kernel<T, T, 2>, grid, block, 0, st, 1, X, h->R, s.H, table_e, urow, ldt, shift_off, scale_off, out);
+    case 4: return launch(h, lnmod_kernel<T, T, 4>, grid, block, 0, st, 1, X, h->R, s.H, table_e, urow, ldt, shift_off, scale_off, out);
+    case 8: return launch(h, lnmod_kernel<T, T, 8>, grid, block, 0, st, 1, X, h->R, s.H, table_e, urow, ldt, shift_off, scale_off, out);
+  }
+  return set_err(-1, "dim_h %d unsupported by the LayerNorm kernel (128, 256, 512, 1024)", s.H);
 }
 
 template <typename T>
 static int launch_attn(FmtHandle* h, cudaStream_t st) {
   const ModelShape& s = h->shape;
   const int heads = h->d.num_heads, hd = s.H / heads;
-  const int n_seq = s.nb * s.B, total_warps = n_seq * heads * s.N, warps = 8;
+  const int n_seq = s.nb * s.B, total_warps = n_seq * heads * s.N, warps = 4;
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
-  const unsigned grid = (total_warps + warps - 1) / warps;
+  const dim3 grid((total_warps + warps - 1) / warps), block(warps * 32);
   const T* qkv = static_cast<const T*>(h->QKV.p);
   T* out = static_cast<T*>(h->A2.p);
+  const int win = h->d.attention_window;
   switch (hd) {
-    case 32: band_attention_kernel<T, 1><<<grid, warps * 32, 0, st>>>(qkv, n_seq, s.N, heads, h->d.attention_window, scale, out); break;
-    case 64: band_attention_kernel<T, 2><<<grid, warps * 32, 0, st>>>(qkv, n_seq, s.N, heads, h->d.attention_window, scale, out); break;
-    case 128: band_attention_kernel<T, 4><<<grid, warps * 32, 0, st>>>(qkv, n_seq, s.N, heads, h->d.attention_window, scale, out); break;
-    default: return set_err(-1, "head_dim %d unsupported (32, 64, 128)", hd);
+    case 32: return launch(h, band_attention_kernel<T, 1>, grid, block, 0, st, 1, qkv, n_seq, s.N, heads, win, scale, out);
+    case 64: return launch(h, band_attention_kernel<T, 2>, grid, block, 0, st, 1, qkv, n_seq, s.N, heads, win, scale, out);
+    case 128: return launch(h, band_attention_kernel<T, 4>, grid, block, 0, st, 1, qkv, n_seq, s.N, heads, win, scale, out);
   }
-  LAUNCH_CHECK(); count_launch(h);
-  return 0;
+  return set_err(-1, "head_dim %d unsupported (32, 64, 128)", hd);
 }
 
-// One model evaluation: V[R, W] = FMT.forward over the nb-way batched CFG branches (FMT.py:277-340), inputs y (B,L,W).
+// One model evaluation: V[R, W] = FMT.forward over the nb-way batched CFG branches (FMT.py:277-340).  The x-embedder
+// operand `ax` has already been written by the producer of the ODE state (init_window / cfg_combine / rk_combine / pack_x).
 template <typename T>
-static int enqueue_forward(FmtHandle* h, int table_slot, const float* y, cudaStream_t st) {
+static int enqueue_forward(FmtHandle* h, int table_slot, cudaStream_t st) {
   const ModelShape& s = h->shape;
   const FmtDims& d = h->d;
-  const WindowArgs* wa = static_cast<const WindowArgs*>(h->wargs.p);
   const int R = h->R, H = s.H;
   const T* table_e = static_cast<const T*>(h->table.p) + static_cast<size_t>(table_slot) * h->U * h->NT;
-
-  pack_x_kernel<T><<<s.B * s.N, 128, 0, st>>>(wa, s, y, static_cast<const float*>(h->prevx.p), static_cast<T*>(h->ax.p));
-  LAUNCH_CHECK(); count_launch(h);
   {
     EpiParams ep = epi(EPI_POS, R, H, h->x_emb.b, h->X.p, H, 1);
     ep.pos = h->pos; ep.frames = s.N;
@@ -280,13 +348,12 @@ static int enqueue_forward(FmtHandle* h, int table_slot, const float* y, cudaStr
   return 0;
 }
 
+template <typename T>
 static int launch_combine(FmtHandle* h, int mode, float* dst, const float* dt_ptr, cudaStream_t st) {
   const ModelShape& s = h->shape;
   const size_t n = static_cast<size_t>(s.B) * s.N * s.W;
-  cfg_combine_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(static_cast<const WindowArgs*>(h->wargs.p), s,
-                                                                            static_cast<const float*>(h->V.p), mode, dst, dt_ptr);
-  LAUNCH_CHECK(); count_launch(h);
-  return 0;
+  return launch(h, cfg_combine_kernel<T>, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, 1,
+                static_cast<const WindowArgs*>(h->wargs.p), s, static_cast<const float*>(h->V.p), mode, dst, dt_ptr, static_cast<T*>(h->ax.p));
 }
 
 // The whole window: prepare -> tables -> S steps x stages -> finalize.  This is what gets captured in the graph.
@@ -294,15 +361,17 @@ template <typename T>
 static int enqueue_window(FmtHandle* h, cudaStream_t st) {
   const ModelShape& s = h->shape;
   const WindowArgs* wa = static_cast<const WindowArgs*>(h->wargs.p);
-  const size_t nx = static_cast<size_t>(s.B) * s.L * s.W, nprev = static_cast<size_t>(s.B) * s.P * s.W;
+  const size_t nx = static_cast<size_t>(s.B) * s.L * s.W, nfull = static_cast<size_t>(s.B) * s.N * s.W;
   float* x_state = static_cast<float*>(h->xstate.p);
   float* y_stage = static_cast<float*>(h->ystage.p);
   float* kbuf = static_cast<float*>(h->kbuf.p);
+  T* ax = static_cast<T*>(h->ax.p);
   const float* ddt = static_cast<const float*>(h->ddt.p);
   const int S = h->plan.n_steps, G = h->plan.n_stages;
+  const dim3 gx(static_cast<unsigned>((nx + 255) / 256)), blk(256);
 
-  init_window_kernel<<<static_cast<unsigned>((nx + 255) / 256), 256, 0, st>>>(wa, x_state, nx, static_cast<float*>(h->prevx.p), nprev);
-  LAUNCH_CHECK(); count_launch(h);
+  FMT_OK(launch(h, init_window_kernel<T>, dim3(static_cast<unsigned>((nfull + 255) / 256)), blk, 0, st, 1, wa, s, x_state,
+                static_cast<float*>(h->prevx.p), ax));
   if (S > 0) FMT_OK(enqueue_prepare<T>(h, st));
   for (int step = 0; step < S; ++step) {
     for (int g = 0; g < G; ++g) {
@@ -311,27 +380,22 @@ static int enqueue_window(FmtHandle* h, cudaStream_t st) {
         const int n = (h->n_eval - e) < h->table_chunk ? (h->n_eval - e) : h->table_chunk;
         FMT_OK(enqueue_tables<T>(h, e, n, st));
       }
-      const float* y_in = x_state;
-      if (g > 0) {   // y_g = y0 + dt * sum_j a[g][j] k_j
+      if (g > 0) {   // y_g = y0 + dt * sum_j a[g][j] k_j  (also refreshes the x-embedder operand)
         const float* a = &h->rk_a[g * G];
-        rk_combine_kernel<<<static_cast<unsigned>((nx + 255) / 256), 256, 0, st>>>(x_state, y_stage, kbuf, nx, nx, g, a[0], G > 1 ? a[1] : 0.f,
-                                                                                  G > 2 ? a[2] : 0.f, G > 3 ? a[3] : 0.f, ddt + step);
-        LAUNCH_CHECK(); count_launch(h);
-        y_in = y_stage;
+        FMT_OK(launch(h, rk_combine_kernel<T>, gx, blk, 0, st, 1, s, static_cast<const float*>(x_state), y_stage, static_cast<const float*>(kbuf), nx, nx, g,
+                      a[0], G > 1 ? a[1] : 0.f, G > 2 ? a[2] : 0.f, G > 3 ? a[3] : 0.f, ddt + step, ax));
       }
-      FMT_OK(enqueue_forward<T>(h, e % h->table_chunk, y_in, st));
-      if (G == 1) FMT_OK(launch_combine(h, 2, x_state, ddt + step, st));           // fused CFG + Euler
-      else FMT_OK(launch_combine(h, 1, kbuf + static_cast<size_t>(g) * nx, nullptr, st));
+      FMT_OK(enqueue_forward<T>(h, e % h->table_chunk, st));
+      if (G == 1) FMT_OK(launch_combine<T>(h, 2, x_state, ddt + step, st));           // fused CFG + Euler
+      else FMT_OK(launch_combine<T>(h, 1, kbuf + static_cast<size_t>(g) * nx, nullptr, st));
     }
     if (G > 1) {
       const float* b = h->rk_b.data();
-      rk_combine_kernel<<<static_cast<unsigned>((nx + 255) / 256), 256, 0, st>>>(x_state, x_state, kbuf, nx, nx, G, b[0], G > 1 ? b[1] : 0.f,
-                                                                                G > 2 ? b[2] : 0.f, G > 3 ? b[3] : 0.f, ddt + step);
-      LAUNCH_CHECK(); count_launch(h);
+      FMT_OK(launch(h, rk_combine_kernel<T>, gx, blk, 0, st, 1, s, static_cast<const float*>(x_state), x_state, static_cast<const float*>(kbuf), nx, nx, G,
+                    b[0], G > 1 ? b[1] : 0.f, G > 2 ? b[2] : 0.f, G > 3 ? b[3] : 0.f, ddt + step, ax));
     }
   }
-  finalize_window_kernel<<<static_cast<unsigned>((nx + 255) / 256), 256, 0, st>>>(wa, s, x_state, static_cast<float*>(h->prevx.p));
-  LAUNCH_CHECK(); count_launch(h);
+  FMT_OK(launch(h, finalize_window_kernel, gx, blk, 0, st, 1, wa, s, static_cast<const float*>(x_state), static_cast<float*>(h->prevx.p)));
   return 0;
 }
 
@@ -405,6 +469,10 @@ int32_t fmt_create(const FmtDims* dims, const void* const* wp, int32_t n_ptrs, i
   h->N = d.num_prev_frames + d.frames_per_clip;
   h->Kc = ((d.dim_w + d.dim_a + d.dim_e + 63) / 64) * 64;
   h->NT = d.depth * 6 * d.dim_h + 2 * d.dim_h;
+  if (const char* e = getenv("FMT_PDL")) h->use_pdl = atoi(e) != 0;
+  if (const char* e = getenv("FMT_SKINNY")) h->use_skinny = atoi(e) != 0;
+  if (const char* e = getenv("FMT_SK_CLUSTER")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) h->sk_cluster = v; }
+  if (const char* e = getenv("FMT_SK_CTAS")) { int v = atoi(e); if (v >= 1) h->sk_target_ctas = v; }
   {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -478,7 +546,7 @@ int32_t fmt_destroy(FmtHandle* h) {
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   for (void* p : h->owned) cudaFree(p);
   DevBuf* bufs[] = {&h->cond, &h->cemb, &h->temb, &h->tfreq, &h->th, &h->silu, &h->table, &h->xstate, &h->ystage, &h->kbuf, &h->prevx, &h->ax,
-                    &h->X, &h->A1, &h->QKV, &h->A2, &h->Hm, &h->V, &h->ddt, &h->dteval, &h->wargs, &h->st_rs, &h->st_wa, &h->st_we, &h->st_noise, &h->st_rd};
+                    &h->X, &h->A1, &h->QKV, &h->A2, &h->Hm, &h->V, &h->ddt, &h->dteval, &h->wargs, &h->st_rs, &h->st_wa, &h->st_we, &h->st_noise, &h->st_rd, &h->sk_scratch, &h->sk_counters};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   delete h;
@@ -573,6 +641,17 @@ int32_t fmt_configure(FmtHandle* h, const FmtPlan* p, void* stream) {
   FMT_OK(dev_alloc(h, h->dteval, static_cast<size_t>(ne > 0 ? ne : 1) * 4));
   FMT_OK(dev_alloc(h, h->wargs, sizeof(WindowArgs)));
   CUDA_OK(cudaMemsetAsync(h->prevx.p, 0, h->prevx.bytes, st));
+  if (R <= 256 && p->mode == FMT_MODE_BF16) {
+    size_t maxN = h->NT > d.mlp_hidden ? h->NT : d.mlp_hidden;
+    if (maxN < 3 * H) maxN = 3 * H;
+    const bool fresh = h->sk_scratch.bytes < 256 * maxN * 4 || !h->sk_counters.p;
+    FMT_OK(dev_alloc(h, h->sk_scratch, 256 * maxN * 4));
+    FMT_OK(dev_alloc(h, h->sk_counters, 4096));
+    if (fresh) {
+      CUDA_OK(cudaMemsetAsync(h->sk_scratch.p, 0, h->sk_scratch.bytes, st));
+      CUDA_OK(cudaMemsetAsync(h->sk_counters.p, 0, h->sk_counters.bytes, st));
+    }
+  }
 
   if (ne > 0) {
     // timestep embeddings of every evaluation (FMT.py:294), computed once per plan
@@ -686,13 +765,18 @@ int32_t fmt_velocity(FmtHandle* h, const FmtEval* ev, void* stream) {
   if (h->plan.mode == FMT_MODE_BF16) {
     FMT_OK(enqueue_prepare<bf16>(h, st));
     FMT_OK(enqueue_tables<bf16>(h, ev->eval_index, 1, st));
-    FMT_OK(enqueue_forward<bf16>(h, 0, ev->x, st));
+    FMT_OK(launch(h, pack_x_kernel<bf16>, dim3(s.B * s.N), dim3(128), 0, st, 1, static_cast<const WindowArgs*>(h->wargs.p), s, ev->x,
+                  static_cast<const float*>(h->prevx.p), static_cast<bf16*>(h->ax.p)));
+    FMT_OK(enqueue_forward<bf16>(h, 0, st));
+    FMT_OK(launch_combine<bf16>(h, 0, ev->v_out, nullptr, st));
   } else {
     FMT_OK(enqueue_prepare<float>(h, st));
     FMT_OK(enqueue_tables<float>(h, ev->eval_index, 1, st));
-    FMT_OK(enqueue_forward<float>(h, 0, ev->x, st));
+    FMT_OK(launch(h, pack_x_kernel<float>, dim3(s.B * s.N), dim3(128), 0, st, 1, static_cast<const WindowArgs*>(h->wargs.p), s, ev->x,
+                  static_cast<const float*>(h->prevx.p), static_cast<float*>(h->ax.p)));
+    FMT_OK(enqueue_forward<float>(h, 0, st));
+    FMT_OK(launch_combine<float>(h, 0, ev->v_out, nullptr, st));
   }
-  FMT_OK(launch_combine(h, 0, ev->v_out, nullptr, st));
   return 0;
 }
 
@@ -715,8 +799,24 @@ static int debug_handle(FmtHandle& h) {
 int32_t fmt_debug_gemm_bf16(const void* A, const void* W, const float* bias, float* out, int32_t M, int32_t N, int32_t K, int32_t block_n, void* stream) {
   FmtHandle h;
   FMT_OK(debug_handle(h));
+  h.use_pdl = false;
+  if (const char* e = getenv("FMT_SK_CLUSTER")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) h.sk_cluster = v; }
+  if (const char* e = getenv("FMT_SK_CTAS")) { int v = atoi(e); if (v >= 1) h.sk_target_ctas = v; }
   EpiParams ep = epi(EPI_STORE, M, N, bias, out, N, 1);
-  return gemm_bf16(&h, static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), K, ep, K, static_cast<cudaStream_t>(stream), block_n);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (block_n == -1) {   // skinny path: needs the (zeroed) split-K scratch
+    REQUIRE(M <= 256 && N % 128 == 0 && K % 64 == 0, "skinny GEMM needs M <= 256, N %% 128 == 0, K %% 64 == 0");
+    CUDA_OK(cudaMalloc(&h.sk_scratch.p, static_cast<size_t>(256) * N * 4)); h.sk_scratch.bytes = static_cast<size_t>(256) * N * 4;
+    CUDA_OK(cudaMalloc(&h.sk_counters.p, 4096)); h.sk_counters.bytes = 4096;
+    CUDA_OK(cudaMemsetAsync(h.sk_scratch.p, 0, h.sk_scratch.bytes, st));
+    CUDA_OK(cudaMemsetAsync(h.sk_counters.p, 0, 4096, st));
+    int rc = gemm_bf16(&h, static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), K, ep, K, st, -1);
+    if (rc == 0) rc = gemm_bf16(&h, static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), K, ep, K, st, -1);   // twice: scratch must be left zeroed
+    cudaStreamSynchronize(st);
+    cudaFree(h.sk_scratch.p); cudaFree(h.sk_counters.p);
+    return rc;
+  }
+  return gemm_bf16(&h, static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), K, ep, K, st, block_n);
 }
 
 int32_t fmt_debug_gemm_fp32(const float* A, const float* W, const float* bias, float* out, int32_t M, int32_t N, int32_t K, void* stream) {

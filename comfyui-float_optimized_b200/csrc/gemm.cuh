@@ -163,10 +163,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
+      pdl_wait_prior_grid();
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int m0 = (t % m_tiles) * C::BM, n0 = (t / m_tiles) * BN;
@@ -213,6 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===================== epilogue warps (TMEM -> registers -> global) =====================
     const int quarter = warp & 3;                          // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    pdl_wait_prior_grid();
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int m0 = (t % m_tiles) * C::BM, n0 = (t / m_tiles) * BN;
@@ -245,6 +248,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
                                                         const EpiParams ep, const int K) {
   __shared__ float sA[16][64 + 4];
   __shared__ float sW[16][64 + 4];
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   float acc[4][4] = {};

@@ -43,6 +43,8 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 // ---------------------------------------------------------------------------------------------------------------
 template <typename AT>
 __global__ void cond_gather_kernel(const WindowArgs* __restrict__ wargs, ModelShape s, AT* __restrict__ cond) {
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
   const WindowArgs a = *wargs;
   const int rows = s.nb * s.B * s.N;
   const int row = blockIdx.x;
@@ -113,6 +115,8 @@ __global__ void small_linear_kernel(const float* __restrict__ in, const float* _
 template <typename AT>
 __global__ void silu_cond_kernel(const float* __restrict__ c_emb, const float* __restrict__ t_emb, int e0, int U, int H,
                                  AT* __restrict__ out, size_t total) {
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
   size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= total) return;
   const int h = static_cast<int>(i % H);
@@ -132,6 +136,8 @@ __global__ void silu_cond_kernel(const float* __restrict__ c_emb, const float* _
 template <typename AT>
 __global__ void pack_x_kernel(const WindowArgs* __restrict__ wargs, ModelShape s, const float* __restrict__ y /* (B,L,W) */,
                               const float* __restrict__ prev_x_state /* (B,P,W) */, AT* __restrict__ ax) {
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
   const WindowArgs a = *wargs;
   const int row = blockIdx.x;   // b*N + f
   const int b = row / s.N, f = row % s.N;
@@ -149,39 +155,45 @@ __global__ void pack_x_kernel(const WindowArgs* __restrict__ wargs, ModelShape s
 // LayerNorm (eps 1e-6, no affine) + framewise modulate  x*(1+scale)+shift   (FMT.py:157,168-169,174-175,197)
 // One warp per row; statistics in fp32 (two-pass).
 // ---------------------------------------------------------------------------------------------------------------
-template <typename AT, typename TT>
+template <typename AT, typename TT, int NV /* H / 128 float4 per lane */>
 __global__ void lnmod_kernel(const float* __restrict__ X, int rows, int H, const TT* __restrict__ table, const int* __restrict__ urow,
                              long long ldt, long long shift_off, long long scale_off, AT* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* x = X + static_cast<size_t>(row) * H;
-  float sum = 0.f;
-  for (int j = lane * 4; j < H; j += 128) {
-    const float4 t = *reinterpret_cast<const float4*>(x + j);
-    sum += (t.x + t.y) + (t.z + t.w);
+  const TT* trow = table + static_cast<size_t>(urow ? urow[row] : row) * ldt;
+  float4 xv[NV];
+  float sh[NV][4], sc[NV][4];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) xv[i] = *reinterpret_cast<const float4*>(x + lane * 4 + i * 128);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {       // issued before the reductions so their latency overlaps the shuffles
+    VecIO<TT, 4>::load(trow + shift_off + lane * 4 + i * 128, sh[i]);
+    VecIO<TT, 4>::load(trow + scale_off + lane * 4 + i * 128, sc[i]);
   }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) sum += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float mean = sum / static_cast<float>(H);
   float var = 0.f;
-  for (int j = lane * 4; j < H; j += 128) {
-    const float4 t = *reinterpret_cast<const float4*>(x + j);
-    const float d0 = t.x - mean, d1 = t.y - mean, d2 = t.z - mean, d3 = t.w - mean;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float d0 = xv[i].x - mean, d1 = xv[i].y - mean, d2 = xv[i].z - mean, d3 = xv[i].w - mean;
     var += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
   const float rstd = rsqrtf(var / static_cast<float>(H) + 1e-6f);
-  const TT* trow = table + static_cast<size_t>(urow ? urow[row] : row) * ldt;
-  for (int j = lane * 4; j < H; j += 128) {
-    const float4 t = *reinterpret_cast<const float4*>(x + j);
-    float sh[4], sc[4];
-    VecIO<TT, 4>::load(trow + shift_off + j, sh);
-    VecIO<TT, 4>::load(trow + scale_off + j, sc);
-    float v[4] = {(t.x - mean) * rstd, (t.y - mean) * rstd, (t.z - mean) * rstd, (t.w - mean) * rstd};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = fmaf(v[k], 1.f + sc[k], sh[k]);
-    VecIO<AT, 4>::store(out + static_cast<size_t>(row) * H + j, v);
+  for (int i = 0; i < NV; ++i) {
+    float v[4] = {(xv[i].x - mean) * rstd, (xv[i].y - mean) * rstd, (xv[i].z - mean) * rstd, (xv[i].w - mean) * rstd};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = fmaf(v[k], 1.f + sc[i][k], sh[i][k]);
+    VecIO<AT, 4>::store(out + static_cast<size_t>(row) * H + lane * 4 + i * 128, v);
   }
 }
 
@@ -190,40 +202,74 @@ __global__ void lnmod_kernel(const float* __restrict__ X, int rows, int H, const
 // One warp per (sequence, head, query row); the <= 2w+1 scores live in registers of the whole warp
 // (dot products reduced with warp shuffles, softmax in fp32).  qkv columns: [q | k | v], each head-major.
 // ---------------------------------------------------------------------------------------------------------------
+template <typename AT, int VPL> struct RowVec;     // VPL consecutive elements of one lane, loaded with one instruction
+template <> struct RowVec<float, 1> { static __device__ __forceinline__ void load(const float* p, float (&v)[1]) { v[0] = *p; } };
+template <> struct RowVec<float, 2> { static __device__ __forceinline__ void load(const float* p, float (&v)[2]) { float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; } };
+template <> struct RowVec<float, 4> { static __device__ __forceinline__ void load(const float* p, float (&v)[4]) { float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; } };
+template <> struct RowVec<__nv_bfloat16, 1> { static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[1]) { v[0] = __bfloat162float(*p); } };
+template <> struct RowVec<__nv_bfloat16, 2> { static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[2]) { __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(p); v[0] = __low2float(t); v[1] = __high2float(t); } };
+template <> struct RowVec<__nv_bfloat16, 4> { static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) { VecIO<__nv_bfloat16, 4>::load(p, v); } };
+
 template <typename AT, int VPL /* head_dim / 32 */>
 __global__ void band_attention_kernel(const AT* __restrict__ qkv, int n_seq, int N, int heads, int window, float scale,
                                       AT* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
   const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (gw >= n_seq * heads * N) return;
   const int i = gw % N, h = (gw / N) % heads, sq = gw / (N * heads);
-  const int hd = VPL * 32, Hd = heads * hd, ld = 3 * Hd;
-  const AT* base = qkv + static_cast<size_t>(sq) * N * ld;
+  constexpr int hd = VPL * 32;
+  const int Hd = heads * hd, ld = 3 * Hd;
+  const AT* base = qkv + static_cast<size_t>(sq) * N * ld + h * hd + lane * VPL;
   float q[VPL];
-#pragma unroll
-  for (int k = 0; k < VPL; ++k) q[k] = to_f32<AT>(base[static_cast<size_t>(i) * ld + h * hd + lane * VPL + k]) * scale;
+  RowVec<AT, VPL>::load(base + static_cast<size_t>(i) * ld, q);
   const int j0 = max(0, i - window), j1 = min(N - 1, i + window);
   float mx = -INFINITY, den = 0.f, acc[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) acc[k] = 0.f;
-  for (int j = j0; j <= j1; ++j) {        // online softmax over the band
-    const AT* kr = base + static_cast<size_t>(j) * ld + Hd + h * hd + lane * VPL;
-    float s = 0.f;
+  constexpr int KB = 5;                     // keys per batch: the default band (window 2) is one batch
+  for (int jb = j0; jb <= j1; jb += KB) {
+    float kv[KB][VPL], vv[KB][VPL], s[KB];
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) s = fmaf(q[k], to_f32<AT>(kr[k]), s);
+    for (int t = 0; t < KB; ++t) {          // all loads of the batch are issued before any use
+      const int j = min(jb + t, j1);
+      RowVec<AT, VPL>::load(base + static_cast<size_t>(j) * ld + Hd, kv[t]);
+      RowVec<AT, VPL>::load(base + static_cast<size_t>(j) * ld + 2 * Hd, vv[t]);
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float nmx = fmaxf(mx, s);
-    const float corr = expf(mx - nmx), p = expf(s - nmx);
-    den = den * corr + p;
-    const AT* vr = kr + Hd;
+    for (int t = 0; t < KB; ++t) {
+      float d = 0.f;
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) acc[k] = fmaf(acc[k], corr, p * to_f32<AT>(vr[k]));
-    mx = nmx;
+      for (int k = 0; k < VPL; ++k) d = fmaf(q[k], kv[t][k], d);
+      s[t] = d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int t = 0; t < KB; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], o);
+#pragma unroll
+    for (int t = 0; t < KB; ++t) {          // online softmax over the band, fp32
+      if (jb + t <= j1) {
+        const float sc = s[t] * scale;
+        const float nmx = fmaxf(mx, sc);
+        const float corr = expf(mx - nmx), p = expf(sc - nmx);
+        den = den * corr + p;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) acc[k] = fmaf(acc[k], corr, p * vv[t][k]);
+        mx = nmx;
+      }
+    }
   }
   const float inv = 1.f / den;
-  AT* o = out + (static_cast<size_t>(sq) * N + i) * Hd + h * hd + lane * VPL;
+  float o[VPL];
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) o[k] = from_f32<AT>(acc[k] * inv);
+  for (int k = 0; k < VPL; ++k) o[k] = acc[k] * inv;
+  AT* op = out + (static_cast<size_t>(sq) * N + i) * Hd + h * hd + lane * VPL;
+  if constexpr (VPL == 4) VecIO<AT, 4>::store(op, reinterpret_cast<float(&)[4]>(o));
+  else {
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) op[k] = from_f32<AT>(o[k]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -240,11 +286,22 @@ __device__ __forceinline__ float cfg_combine(const float* __restrict__ V, size_t
   return tu + r * (u - tu) + a * (ao - u) + e * (c - ao);
 }
 
+// Every producer of an ODE state also writes the x-embedder operand rows of that state (replicated over the CFG
+// branches, FMT.py:363): ax[(br, b, P + f), :] = bf16(y[b, f, :]).  Context rows are written once per window.
+template <typename AT>
+__device__ __forceinline__ void store_ax(const ModelShape& s, AT* __restrict__ ax, int b, int f_full, int j, float v) {
+  const AT t = from_f32<AT>(v);
+  for (int br = 0; br < s.nb; ++br) ax[((static_cast<size_t>(br) * s.B + b) * s.N + f_full) * s.W + j] = t;
+}
+
 // mode 0: v_full[b, f, :] = combined, all N frames (fmt_velocity)
 // mode 1: k_out[b, f-P, :] = combined, current frames only (RK stage derivative)
-// mode 2: y[b, f-P, :] += dt * combined   (fused Euler update, torchdiffeq euler: y1 = y0 + dt*f(t0,y0))
+// mode 2: y[b, f-P, :] += dt * combined   (fused CFG + Euler update, torchdiffeq euler: y1 = y0 + dt*f(t0,y0))
+template <typename AT>
 __global__ void cfg_combine_kernel(const WindowArgs* __restrict__ wargs, ModelShape s, const float* __restrict__ V, int mode,
-                                   float* __restrict__ dst, const float* __restrict__ dt_ptr) {
+                                   float* __restrict__ dst, const float* __restrict__ dt_ptr, AT* __restrict__ ax) {
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
   const WindowArgs a = *wargs;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t per_branch = static_cast<size_t>(s.B) * s.N * s.W;
@@ -257,32 +314,60 @@ __global__ void cfg_combine_kernel(const WindowArgs* __restrict__ wargs, ModelSh
   else {
     const size_t o = (static_cast<size_t>(b) * s.L + (f - s.P)) * s.W + j;
     if (mode == 1) dst[o] = v;
-    else dst[o] = fmaf(*dt_ptr, v, dst[o]);
+    else {
+      const float y = fmaf(*dt_ptr, v, dst[o]);
+      dst[o] = y;
+      store_ax<AT>(s, ax, b, f, j, y);
+    }
   }
 }
 
-// y_out = y0 + dt * sum_j coef[j] * k_j   (explicit Runge-Kutta stage / final combination)
-__global__ void rk_combine_kernel(const float* __restrict__ y0, float* __restrict__ y_out, const float* __restrict__ k, size_t n,
-                                  size_t k_stride, int n_k, float c0, float c1, float c2, float c3, const float* __restrict__ dt_ptr) {
+// y_out = y0 + dt * sum_j coef[j] * k_j   (explicit Runge-Kutta stage / final combination); also refreshes ax
+template <typename AT>
+__global__ void rk_combine_kernel(ModelShape s, const float* __restrict__ y0, float* __restrict__ y_out, const float* __restrict__ k,
+                                  size_t n, size_t k_stride, int n_k, float c0, float c1, float c2, float c3,
+                                  const float* __restrict__ dt_ptr, AT* __restrict__ ax) {
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float c[4] = {c0, c1, c2, c3};
   float acc = 0.f;
   for (int j = 0; j < n_k; ++j)
     if (c[j] != 0.f) acc = fmaf(c[j], k[j * k_stride + i], acc);
-  y_out[i] = fmaf(*dt_ptr, acc, y0[i]);
+  const float y = fmaf(*dt_ptr, acc, y0[i]);
+  y_out[i] = y;
+  const int j = static_cast<int>(i % s.W), f = static_cast<int>((i / s.W) % s.L), b = static_cast<int>(i / (static_cast<size_t>(s.W) * s.L));
+  store_ax<AT>(s, ax, b, s.P + f, j, y);
 }
 
-// Window prologue / epilogue: x_state <- x0 ; r_d[:, win] <- x_state, prev_x <- last P frames (nodes_adv.py:659-668,690-692)
-__global__ void init_window_kernel(const WindowArgs* __restrict__ wargs, float* __restrict__ x_state, size_t n,
-                                   float* __restrict__ prev_x_state, size_t n_prev) {
+// Window prologue: x_state <- x0, context rows <- prev_x (zero in the first window, nodes_adv.py:591), ax <- [prev_x | x0]
+template <typename AT>
+__global__ void init_window_kernel(const WindowArgs* __restrict__ wargs, ModelShape s, float* __restrict__ x_state,
+                                   float* __restrict__ prev_x_state, AT* __restrict__ ax) {
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
   const WindowArgs a = *wargs;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) x_state[i] = a.x0[i];
-  if (a.first_window && i < n_prev) prev_x_state[i] = 0.f;
+  if (i >= static_cast<size_t>(s.B) * s.N * s.W) return;
+  const int j = static_cast<int>(i % s.W), f = static_cast<int>((i / s.W) % s.N), b = static_cast<int>(i / (static_cast<size_t>(s.W) * s.N));
+  float v;
+  if (f < s.P) {
+    const size_t o = (static_cast<size_t>(b) * s.P + f) * s.W + j;
+    if (a.first_window) { v = 0.f; prev_x_state[o] = 0.f; }
+    else v = prev_x_state[o];
+  } else {
+    const size_t o = (static_cast<size_t>(b) * s.L + (f - s.P)) * s.W + j;
+    v = a.x0[o];
+    x_state[o] = v;
+  }
+  store_ax<AT>(s, ax, b, f, j, v);
 }
+// Window epilogue: r_d[:, window] <- x_state, prev_x <- last P frames (nodes_adv.py:659-668,690-692)
 __global__ void finalize_window_kernel(const WindowArgs* __restrict__ wargs, ModelShape s, const float* __restrict__ x_state,
                                        float* __restrict__ prev_x_state) {
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
   const WindowArgs a = *wargs;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<size_t>(s.B) * s.L * s.W) return;
