@@ -85,7 +85,7 @@ struct FmtHandle {
   DevBuf st_rs, st_wa, st_we, st_noise, st_rd;   // staging for host-located clips
   DevBuf sk_scratch, sk_counters;                // split-K fix-up state of the skinny GEMM (kept all-zero between launches)
   bool use_pdl = true;                           // programmatic dependent launch between graph nodes (FMT_PDL=0 disables)
-  bool use_skinny = true;                        // skinny-M GEMM for M <= 256 (FMT_SKINNY=0 disables)
+  bool use_skinny = false;                       // atomic split-K skinny-M GEMM (FMT_SKINNY=1 enables; measured slower than the tiled path, kept for tests)
   int sk_cluster = 8;                            // cluster size of the skinny GEMM (FMT_SK_CLUSTER)
   int sk_target_ctas = 128;                      // K-split until about this many CTAs (FMT_SK_CTAS)
   size_t ws_bytes = 0;

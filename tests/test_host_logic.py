@@ -1,0 +1,130 @@
+"""CPU tests of the host side: C-ABI library exports, solver schedules, branch selection, option plumbing, loud failure
+without a GPU.  No compute call is made through the library here (no GPU in the build container)."""
+import ctypes as C
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+import cases
+from __graft_entry__ import ROOT, load_package
+from oracle import fmt_oracle as O
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return load_package()
+
+
+def _cabi(pkg):
+    return sys.modules[pkg.__name__ + "._cabi"]
+
+
+def test_library_exports_every_symbol_of_the_header(pkg):
+    hdr = open(os.path.join(ROOT, "include", "fmt_b200.h")).read()
+    declared = set(re.findall(r"FMT_API\s+[\w\s\*]+?\b(fmt_\w+)\s*\(", hdr))
+    assert {"fmt_create", "fmt_destroy", "fmt_configure", "fmt_sample_clip", "fmt_velocity", "fmt_last_error"} <= declared
+    sys.modules[pkg.__name__ + ".build"].build()
+    lib = _cabi(pkg).load_library()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/fmt_b200.h but not exported"
+    assert set(_cabi(pkg)._SIGNATURES) == declared           # the ctypes binding covers exactly the header
+    assert lib.fmt_abi_version() == _cabi(pkg).FMT_ABI_VERSION
+
+
+def test_struct_layouts_match_the_header(pkg):
+    cabi = _cabi(pkg)
+    assert C.sizeof(cabi.FmtDims) == 40
+    assert C.sizeof(cabi.FmtPlan) == 24 + 4 * 8
+    assert cabi.FmtClip.noise.offset == 32 and cabi.FmtClip.T_wa.offset == 48 and cabi.FmtClip.progress.offset == 72
+    assert len(cabi.GLOBAL_KEYS) == cabi.FMT_W_NUM_GLOBAL and len(cabi.BLOCK_KEYS) == cabi.FMT_W_PER_BLOCK
+
+
+def test_no_cpu_fallback(pkg):
+    """Without a CUDA device the product path must fail loudly (never route through the oracle / eager torch)."""
+    model = pkg.FmtModel(cases.weights("small"), target_device="cpu")
+    with pytest.raises(pkg.FmtError):
+        pkg.backend_for(model, "cpu")
+    if not torch.cuda.is_available():
+        d = cases.SMALL_DIMS
+        sd = cases.weights("small")
+        dims = pkg.Dims.from_options({}, sd)
+        with pytest.raises((pkg.FmtError, RuntimeError, AssertionError)):
+            pkg.FmtBackend(sd, dims, "cuda:0")
+    src = open(os.path.join(ROOT, "comfyui-float_optimized_b200", "sampler.py")).read()
+    src += open(os.path.join(ROOT, "comfyui-float_optimized_b200", "nodes.py")).read()
+    assert "oracle" not in src
+
+
+@pytest.mark.parametrize("method", ["euler", "midpoint", "heun2", "heun3", "rk4"])
+@pytest.mark.parametrize("nfe", [1, 2, 5, 10])
+def test_schedule_reproduces_torchdiffeq_fixed_grid(pkg, method, nfe):
+    """The Butcher-tableau schedule handed to the C ABI integrates dy/dt = f(t, y) exactly like the oracle's restatement
+    of torchdiffeq's fixed-grid solvers (same evaluation times, same combination weights)."""
+    s = pkg.build_schedule(nfe, method)
+    assert s["n_steps"] == max(0, nfe - 1) and len(s["t_eval"]) == s["n_steps"] * s["n_stages"]
+    f = lambda t, y: torch.sin(3.0 * t) * y + torch.cos(y) * t      # noqa: E731
+    y0 = torch.linspace(-1, 1, 7, dtype=torch.float64)
+    ref = O.odeint_fixed(f, y0, torch.linspace(0, 1, nfe, dtype=torch.float32).double(), method)
+    G, y = s["n_stages"], y0.clone()
+    for i in range(s["n_steps"]):
+        ks = []
+        for g in range(G):
+            yg = y + s["dt"][i] * sum(s["a"][g * G + j] * ks[j] for j in range(g)) if g else y
+            ks.append(f(torch.tensor(s["t_eval"][i * G + g], dtype=torch.float64), yg))
+        y = y + s["dt"][i] * sum(s["b"][j] * ks[j] for j in range(G))
+    assert torch.allclose(y, ref, rtol=1e-6, atol=1e-7), (y - ref).abs().max()
+
+
+def test_unknown_solver_raises(pkg):
+    with pytest.raises(ValueError):
+        pkg.build_schedule(10, "dopri5")
+
+
+def test_branch_selection_mirrors_forward_with_cfv(pkg):
+    assert pkg.n_branches_for(1.0, 1.0, 1.0, False) == 1 and pkg.n_branches_for(1.0, 1.0, 1.0, True) == 1   # FMT.py:346,400
+    assert pkg.n_branches_for(2.0, 1.0, 1.0, False) == 3 and pkg.n_branches_for(1.0, 1.0, 3.0, False) == 3
+    assert pkg.n_branches_for(2.0, 1.0, 1.0, True) == 4 and pkg.n_branches_for(1.0, 0.5, 1.0, True) == 4
+
+
+def test_dims_follow_the_checkpoint(pkg):
+    sd = cases.weights("small")
+    d, s = pkg.Dims.from_options(pkg.BaseOptions(), sd), cases.SMALL_DIMS
+    assert (d.dim_h, d.dim_w, d.dim_a, d.fmt_depth, d.mlp_hidden) == (s.dim_h, s.dim_w, s.dim_a, s.fmt_depth, s.mlp_hidden)
+    full = pkg.Dims.from_options(pkg.BaseOptions())
+    assert (full.dim_h, full.frames_per_clip, full.num_prev_frames, full.attention_window) == (1024, 50, 10, 2)
+
+
+def test_node_surface_matches_reference(pkg):
+    """UNIQUE_NAME / FUNCTION / RETURN_TYPES / input names of nodes_vadv.py:534-623 and nodes_adv.py:697-723."""
+    va = pkg.FloatSampleMotionSequenceRD_VA
+    assert va.UNIQUE_NAME == "FloatSampleMotionSequenceRD_VA" and va.FUNCTION == "sample_rd_sequence_va"
+    assert va.RETURN_TYPES == ("TORCH_TENSOR", "FLOAT_FMT_MODEL") and va.CATEGORY == "FLOAT/Very Advanced"
+    req = va.INPUT_TYPES()["required"]
+    assert list(req) == ["r_s_latent", "wa_latent", "audio_num_frames", "we_latent", "float_fmt_model", "a_cfg_scale", "r_cfg_scale",
+                         "e_cfg_scale", "include_r_cfg", "nfe", "torchdiffeq_ode_method", "ode_atol", "ode_rtol", "audio_dropout_prob",
+                         "ref_dropout_prob", "emotion_dropout_prob", "fix_noise_seed", "seed"]
+    assert req["torchdiffeq_ode_method"][0] == ["euler", "midpoint", "rk4", "heun2", "heun3"]
+    assert req["nfe"][1] == {"default": 10, "min": 1, "max": 1000} and req["seed"][1]["default"] == 15
+    adv = pkg.FloatSampleMotionSequenceRD
+    assert adv.UNIQUE_NAME == "FloatSampleMotionSequenceRD" and adv.FUNCTION == "sample_rd_sequence"
+    assert list(adv.INPUT_TYPES()["required"]) == ["r_s_latent", "wa_latent", "audio_num_frames", "we_latent", "float_pipe", "a_cfg_scale",
+                                                   "e_cfg_scale", "seed"]
+    assert set(pkg.NODE_CLASS_MAPPINGS) == {"FloatSampleMotionSequenceRD_VA", "FloatSampleMotionSequenceRD"}
+
+
+def test_node_validation_runs_before_any_device_work(pkg):
+    model = pkg.FmtModel(cases.weights("small"), target_device="cpu")
+    node = pkg.FloatSampleMotionSequenceRD_VA()
+    r_s, wa, we = torch.zeros(2, 32), torch.zeros(2, 20, 32), torch.zeros(2, 1, 7)
+    args = (2.0, 1.0, 1.0, False, 2, "euler", 1e-5, 1e-5, 0.3, 0.3, 0.3, True, 3)
+    with pytest.raises(TypeError):
+        node.sample_rd_sequence_va(r_s.numpy(), wa, we, 20, model, *args)
+    with pytest.raises(ValueError):
+        node.sample_rd_sequence_va(r_s[:1], wa, we, 20, model, *args)
+    before = (model.opt.audio_dropout_prob, model.opt.ref_dropout_prob, model.opt.emotion_dropout_prob)
+    with pytest.raises(pkg.FmtError):          # CPU target: no fallback; dropout probs restored (nodes_vadv.py:729-735)
+        node.sample_rd_sequence_va(r_s, wa, we, 20, model, *args)
+    assert before == (model.opt.audio_dropout_prob, model.opt.ref_dropout_prob, model.opt.emotion_dropout_prob)
