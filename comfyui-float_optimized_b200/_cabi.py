@@ -64,6 +64,8 @@ _SIGNATURES = {
     "fmt_velocity": (C.c_int32, [C.c_void_p, C.POINTER(FmtEval), C.c_void_p]),
     "fmt_launch_count": (C.c_int64, [C.c_void_p, C.c_int32]),
     "fmt_graph_kernel_nodes": (C.c_int32, [C.c_void_p]),
+    "fmt_window_kernel_status": (C.c_int32, [C.c_void_p]),
+    "fmt_debug_window_trace": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
     "fmt_debug_gemm_bf16": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "fmt_debug_gemm_fp32": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }

@@ -6,6 +6,7 @@
 #include "../../include/fmt_b200.h"
 #include "kernels.cuh"
 #include "skinny.cuh"
+#include "window.cuh"
 
 #include <cstdlib>
 
@@ -90,6 +91,15 @@ struct FmtHandle {
   int sk_target_ctas = 128;                      // K-split until about this many CTAs (FMT_SK_CTAS)
   size_t ws_bytes = 0;
 
+  // persistent window kernel (window.cuh): used when the plan has <= 256 token rows in bf16 mode
+  bool use_window = true;                        // FMT_WINDOW=0 disables (falls back to one kernel per op)
+  bool window_active = false;
+  int win_pk[4] = {0, 0, 0, 0};                  // K-split overrides for qkv / proj / fc1 / fc2 (FMT_WIN_PK="q,p,1,2"; 0 = auto)
+  DevBuf win_params, win_tmaps, win_acc, win_bar, win_trace;
+  int win_trace_stride = 0;
+  int* win_err_host = nullptr;                   // mapped pinned int: which bounded spin tripped (0 = none)
+  int* win_err_dev = nullptr;
+
   cudaGraphExec_t graph_exec = nullptr;
   int graph_nodes = 0;
   long long launches = 0;
@@ -152,6 +162,18 @@ static int make_tmap(FmtHandle* h, CUtensorMap* m, const void* ptr, int rows, in
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_err(-3, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d box=%d ptr=%p", (int)r, rows, cols, ld_elems, box_rows, ptr);
+  return 0;
+}
+
+static int make_tmap_ex(FmtHandle* h, CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int elem_bytes, int rows, int cols, int ld_elems,
+                        int box_cols, int box_rows, CUtensorMapSwizzle sw) {
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld_elems) * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(m, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(-3, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d box=%dx%d ptr=%p", (int)r, rows, cols, ld_elems, box_cols, box_rows, ptr);
   return 0;
 }
 
@@ -356,6 +378,138 @@ static int launch_combine(FmtHandle* h, int mode, float* dst, const float* dt_pt
                 static_cast<const WindowArgs*>(h->wargs.p), s, static_cast<const float*>(h->V.p), mode, dst, dt_ptr, static_cast<T*>(h->ax.p));
 }
 
+// ------------------------------------------------------------------------------------------------ persistent window kernel
+static bool window_eligible(const FmtHandle* h, const FmtPlan* p) {
+  const FmtDims& d = h->d;
+  const int R = p->n_branches * p->batch * (d.num_prev_frames + d.frames_per_clip);
+  const int nv = d.dim_h / 128;
+  return h->use_window && p->mode == FMT_MODE_BF16 && R <= 256 && p->n_steps * p->n_stages >= 1 && d.depth <= WIN_MAX_DEPTH &&
+         (nv == 1 || nv == 2 || nv == 4 || nv == 8) && d.mlp_hidden % 64 == 0 && d.dim_w % 64 == 0;
+}
+
+// Builds the device-side description of the window kernel: tensor maps, GEMM item plan, pointers.  Called by fmt_configure
+// after the workspace exists.
+static int setup_window(FmtHandle* h, cudaStream_t st) {
+  const ModelShape& s = h->shape;
+  const FmtDims& d = h->d;
+  const int R = h->R, H = s.H, M4 = d.mlp_hidden, W = s.W, D = d.depth;
+  const int Rp = R <= 64 ? 64 : R <= 128 ? 128 : R <= 192 ? 192 : 256;
+  const int n_gemms = 2 + 4 * D;
+  const int grid = h->num_sms;
+  WinParams wp{};
+  wp.s = s; wp.R = R; wp.Rp = Rp; wp.depth = D; wp.heads = d.num_heads; wp.window = d.attention_window; wp.mlp_hidden = M4; wp.NT = h->NT;
+  wp.n_steps = h->plan.n_steps; wp.n_stages = h->plan.n_stages; wp.n_gemms = n_gemms;
+
+  // accumulator arena: [Pacc (R,H) | QKVacc (R,3H) | Hacc (R,M4) | Vacc (R,W)] fp32, zeroed by one memset per window
+  const size_t n_p = static_cast<size_t>(R) * H, n_q = static_cast<size_t>(R) * 3 * H, n_h = static_cast<size_t>(R) * M4, n_v = static_cast<size_t>(R) * W;
+  FMT_OK(dev_alloc(h, h->win_acc, (n_p + n_q + n_h + n_v) * 4));
+  FMT_OK(dev_alloc(h, h->win_bar, 256));
+  FMT_OK(dev_alloc(h, h->win_params, sizeof(WinParams)));
+  const int n_maps = n_gemms + 8;
+  FMT_OK(dev_alloc(h, h->win_tmaps, static_cast<size_t>(n_maps) * sizeof(CUtensorMap)));
+  if (!h->win_err_host) {
+    CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&h->win_err_host), sizeof(int), cudaHostAllocMapped));
+    *h->win_err_host = 0;
+    CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->win_err_dev), h->win_err_host, 0));
+  }
+  float* arena = static_cast<float*>(h->win_acc.p);
+  wp.Pacc = arena; wp.QKVacc = arena + n_p; wp.Hacc = wp.QKVacc + n_q; wp.Vacc = wp.Hacc + n_h;
+  wp.X = static_cast<float*>(h->X.p);
+  wp.A1 = static_cast<bf16*>(h->A1.p); wp.A2 = static_cast<bf16*>(h->A2.p); wp.Hm = static_cast<bf16*>(h->Hm.p); wp.ax = static_cast<bf16*>(h->ax.p);
+  wp.table = static_cast<const bf16*>(h->table.p);
+  wp.b_x = h->x_emb.b; wp.pos = h->pos; wp.b_dec = h->dec.b;
+  for (int i = 0; i < D; ++i) { wp.b_qkv[i] = h->qkv[i].b; wp.b_proj[i] = h->proj[i].b; wp.b_fc1[i] = h->fc1[i].b; wp.b_fc2[i] = h->fc2[i].b; }
+  wp.x_state = static_cast<float*>(h->xstate.p); wp.kbuf = static_cast<float*>(h->kbuf.p); wp.ddt = static_cast<const float*>(h->ddt.p);
+  for (int i = 0; i < h->plan.n_stages * h->plan.n_stages; ++i) wp.rk_a[i] = h->rk_a[i];
+  for (int i = 0; i < h->plan.n_stages; ++i) wp.rk_b[i] = h->rk_b[i];
+  wp.wargs = static_cast<const WindowArgs*>(h->wargs.p);
+  wp.bar_counter = static_cast<unsigned*>(h->win_bar.p);
+  wp.err_flag = h->win_err_dev;
+  wp.tmaps = static_cast<const CUtensorMap*>(h->win_tmaps.p);
+  wp.w_lookahead = 1;
+  if (const char* e = getenv("FMT_WIN_LA")) wp.w_lookahead = atoi(e);
+  if (getenv("FMT_WIN_TRACE") && atoi(getenv("FMT_WIN_TRACE")) != 0) {
+    h->win_trace_stride = h->n_eval * (4 + 8 * D);
+    FMT_OK(dev_alloc(h, h->win_trace, static_cast<size_t>(grid) * h->win_trace_stride * 6 * sizeof(long long)));
+    CUDA_OK(cudaMemsetAsync(h->win_trace.p, 0, h->win_trace.bytes, st));
+    wp.trace = static_cast<long long*>(h->win_trace.p); wp.trace_stride = h->win_trace_stride;
+  }
+
+  std::vector<CUtensorMap> maps(n_maps);
+  const int A_AX = n_gemms, A_A1 = n_gemms + 1, A_A2 = n_gemms + 2, A_HM = n_gemms + 3;
+  const int C_P = n_gemms + 4, C_Q = n_gemms + 5, C_H = n_gemms + 6, C_V = n_gemms + 7;
+  const CUtensorMapDataType BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  FMT_OK(make_tmap_ex(h, &maps[A_AX], wp.ax, BF, 2, R, W, W, 64, Rp, CU_TENSOR_MAP_SWIZZLE_128B));
+  FMT_OK(make_tmap_ex(h, &maps[A_A1], wp.A1, BF, 2, R, H, H, 64, Rp, CU_TENSOR_MAP_SWIZZLE_128B));
+  FMT_OK(make_tmap_ex(h, &maps[A_A2], wp.A2, BF, 2, R, H, H, 64, Rp, CU_TENSOR_MAP_SWIZZLE_128B));
+  FMT_OK(make_tmap_ex(h, &maps[A_HM], wp.Hm, BF, 2, R, M4, M4, 64, Rp, CU_TENSOR_MAP_SWIZZLE_128B));
+  FMT_OK(make_tmap_ex(h, &maps[C_P], wp.Pacc, F32, 4, R, H, H, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
+  FMT_OK(make_tmap_ex(h, &maps[C_Q], wp.QKVacc, F32, 4, R, 3 * H, 3 * H, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
+  FMT_OK(make_tmap_ex(h, &maps[C_H], wp.Hacc, F32, 4, R, M4, M4, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
+  FMT_OK(make_tmap_ex(h, &maps[C_V], wp.Vacc, F32, 4, R, W, W, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
+
+  int next_off = 0;
+  auto plan_gemm = [&](int g, const Linear& L, int tm_a, int tm_acc, int pk_override) -> int {
+    WinGemm& G = wp.gemms[g];
+    G.tm_w = g; G.tm_a = tm_a; G.tm_acc = tm_acc;
+    G.n_ft = (L.N + 127) / 128;
+    G.nkb = (L.K + 63) / 64;
+    REQUIRE(G.n_ft <= grid, "window kernel: %d feature tiles > %d SMs", G.n_ft, grid);
+    int pk = grid / G.n_ft;
+    if (pk > G.nkb) pk = G.nkb;
+    if (pk_override > 0 && pk_override <= pk) pk = pk_override;
+    G.pk = pk;
+    G.cta_off = next_off;
+    next_off = (next_off + G.n_ft * pk) % grid;
+    return make_tmap_ex(h, &maps[g], L.w16, BF, 2, L.N, L.K, L.K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+  };
+  FMT_OK(plan_gemm(0, h->x_emb, A_AX, C_P, 0));
+  for (int i = 0; i < D; ++i) {
+    FMT_OK(plan_gemm(1 + 4 * i, h->qkv[i], A_A1, C_Q, h->win_pk[0]));
+    FMT_OK(plan_gemm(2 + 4 * i, h->proj[i], A_A2, C_P, h->win_pk[1]));
+    FMT_OK(plan_gemm(3 + 4 * i, h->fc1[i], A_A1, C_H, h->win_pk[2]));
+    FMT_OK(plan_gemm(4 + 4 * i, h->fc2[i], A_HM, C_P, h->win_pk[3]));
+  }
+  FMT_OK(plan_gemm(1 + 4 * D, h->dec, A_A1, C_V, 0));
+  CUDA_OK(cudaMemcpyAsync(h->win_tmaps.p, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(h->win_params.p, &wp, sizeof(WinParams), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaStreamSynchronize(st));   // `maps` / `wp` are stack objects
+  return 0;
+}
+
+template <int NV>
+static int launch_window_nv(FmtHandle* h, cudaStream_t st) {
+  static bool attr_set[64] = {};
+  if (!attr_set[h->device & 63]) {
+    CUDA_OK(cudaFuncSetAttribute(fmt_window_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM_BYTES));
+    attr_set[h->device & 63] = true;
+  }
+  int occ = 0;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fmt_window_kernel<NV>, WIN_THREADS, WIN_SMEM_BYTES));
+  REQUIRE(occ >= 1, "window kernel does not fit on an SM (%d B smem)", WIN_SMEM_BYTES);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(h->num_sms); cfg.blockDim = dim3(WIN_THREADS); cfg.dynamicSmemBytes = WIN_SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: the kernel synchronises across the grid
+  attrs[0].val.cooperative = 1;
+  cfg.attrs = attrs; cfg.numAttrs = 1;
+  CUDA_OK(cudaLaunchKernelEx(&cfg, fmt_window_kernel<NV>, static_cast<const WinParams*>(h->win_params.p)));
+  count_launch(h);
+  return 0;
+}
+
+static int launch_window(FmtHandle* h, cudaStream_t st) {
+  CUDA_OK(cudaMemsetAsync(h->win_acc.p, 0, h->win_acc.bytes, st));
+  CUDA_OK(cudaMemsetAsync(h->win_bar.p, 0, h->win_bar.bytes, st));
+  switch (h->shape.H / 128) {
+    case 1: return launch_window_nv<1>(h, st);
+    case 2: return launch_window_nv<2>(h, st);
+    case 4: return launch_window_nv<4>(h, st);
+    case 8: return launch_window_nv<8>(h, st);
+  }
+  return set_err(-1, "window kernel: dim_h %d unsupported", h->shape.H);
+}
+
 // The whole window: prepare -> tables -> S steps x stages -> finalize.  This is what gets captured in the graph.
 template <typename T>
 static int enqueue_window(FmtHandle* h, cudaStream_t st) {
@@ -373,6 +527,13 @@ static int enqueue_window(FmtHandle* h, cudaStream_t st) {
   FMT_OK(launch(h, init_window_kernel<T>, dim3(static_cast<unsigned>((nfull + 255) / 256)), blk, 0, st, 1, wa, s, x_state,
                 static_cast<float*>(h->prevx.p), ax));
   if (S > 0) FMT_OK(enqueue_prepare<T>(h, st));
+  if (h->window_active && S > 0) {
+    // small-R plan: every evaluation of the window runs inside ONE persistent kernel (window.cuh)
+    FMT_OK(enqueue_tables<T>(h, 0, h->n_eval, st));
+    FMT_OK(launch_window(h, st));
+    FMT_OK(launch(h, finalize_window_kernel, gx, blk, 0, st, 1, wa, s, static_cast<const float*>(x_state), static_cast<float*>(h->prevx.p)));
+    return 0;
+  }
   for (int step = 0; step < S; ++step) {
     for (int g = 0; g < G; ++g) {
       const int e = step * G + g;
@@ -471,6 +632,8 @@ int32_t fmt_create(const FmtDims* dims, const void* const* wp, int32_t n_ptrs, i
   h->NT = d.depth * 6 * d.dim_h + 2 * d.dim_h;
   if (const char* e = getenv("FMT_PDL")) h->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("FMT_SKINNY")) h->use_skinny = atoi(e) != 0;
+  if (const char* e = getenv("FMT_WINDOW")) h->use_window = atoi(e) != 0;
+  if (const char* e = getenv("FMT_WIN_PK")) sscanf(e, "%d,%d,%d,%d", &h->win_pk[0], &h->win_pk[1], &h->win_pk[2], &h->win_pk[3]);
   if (const char* e = getenv("FMT_SK_CLUSTER")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) h->sk_cluster = v; }
   if (const char* e = getenv("FMT_SK_CTAS")) { int v = atoi(e); if (v >= 1) h->sk_target_ctas = v; }
   {
@@ -546,9 +709,11 @@ int32_t fmt_destroy(FmtHandle* h) {
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   for (void* p : h->owned) cudaFree(p);
   DevBuf* bufs[] = {&h->cond, &h->cemb, &h->temb, &h->tfreq, &h->th, &h->silu, &h->table, &h->xstate, &h->ystage, &h->kbuf, &h->prevx, &h->ax,
-                    &h->X, &h->A1, &h->QKV, &h->A2, &h->Hm, &h->V, &h->ddt, &h->dteval, &h->wargs, &h->st_rs, &h->st_wa, &h->st_we, &h->st_noise, &h->st_rd, &h->sk_scratch, &h->sk_counters};
+                    &h->X, &h->A1, &h->QKV, &h->A2, &h->Hm, &h->V, &h->ddt, &h->dteval, &h->wargs, &h->st_rs, &h->st_wa, &h->st_we, &h->st_noise, &h->st_rd, &h->sk_scratch, &h->sk_counters,
+                    &h->win_params, &h->win_tmaps, &h->win_acc, &h->win_bar, &h->win_trace};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
+  if (h->win_err_host) cudaFreeHost(h->win_err_host);
   delete h;
   return 0;
 }
@@ -562,6 +727,18 @@ int64_t fmt_launch_count(const FmtHandle* hc, int32_t reset) {
   return v;
 }
 int32_t fmt_graph_kernel_nodes(const FmtHandle* h) { return h ? h->graph_nodes : 0; }
+int64_t fmt_debug_window_trace(const FmtHandle* h, int64_t* out, int64_t max_elems) {
+  if (!h || !h->win_trace.p) return 0;
+  const int64_t n = static_cast<int64_t>(h->num_sms) * h->win_trace_stride * 6;
+  if (out != nullptr && max_elems >= n) {
+    if (cudaMemcpy(out, h->win_trace.p, n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  }
+  return n;
+}
+int32_t fmt_window_kernel_status(const FmtHandle* h) {
+  if (!h || !h->window_active) return -1;
+  return h->win_err_host ? *h->win_err_host : 0;
+}
 
 static bool same_plan(const FmtHandle* h, const FmtPlan* p) {
   if (!h->configured) return false;
@@ -666,6 +843,9 @@ int32_t fmt_configure(FmtHandle* h, const FmtPlan* p, void* stream) {
     LAUNCH_CHECK(); count_launch(h);
     CUDA_OK(cudaStreamSynchronize(st));   // t_eval/dt host vectors may be reassigned by the next configure
   }
+
+  h->window_active = window_eligible(h, p) && h->table_chunk == ne;
+  if (h->window_active) FMT_OK(setup_window(h, st));
 
   // capture one window as a CUDA graph
   {

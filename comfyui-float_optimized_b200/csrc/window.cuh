@@ -1,0 +1,736 @@
+// Persistent window kernel for the weight-streaming regime (R = nb*B*60 <= 256 token rows, i.e. one or two clips per GPU).
+//
+// One launch runs EVERY model evaluation of a sampling window (S Euler steps, or S x stages for the RK solvers): 148
+// CTAs (one per SM) walk the same list of ~68 stages per evaluation and meet at a grid barrier between stages.
+//
+//   * GEMM stage   acc[R, N] += A[R, K] . W[N, K]^T   weight-stationary + split-K: item (ft, ks) = 128 output features x a
+//                  range of 64-wide K blocks; the weight tile is the UMMA A operand (M = 128), ALL token rows are the UMMA
+//                  B operand (N = Rp), so every weight byte is pulled from HBM exactly once by exactly one SM.  The fp32
+//                  partial tile goes TMEM -> registers -> smem -> L2 with TMA reduce-add (cp.reduce.async.bulk.tensor), so
+//                  split-K costs one pass over the tile and no atomics from the SM.
+//   * weight ring  warp 0 is a free-running TMA producer: it walks this CTA's items of ALL stages and evaluations and
+//                  keeps an 80 KB ring of weight tiles full.  It never waits for a grid barrier, so the HBM weight stream
+//                  keeps flowing while the other warps wait on barriers, activations or epilogues.
+//   * SIMT stages  consume the fp32 accumulators and produce the next bf16 operand: ROW (bias, gate, residual, LayerNorm,
+//                  AdaLN modulate), ATTN (band attention), GELU, COMB (CFG combine + ODE update).  Each consumer zeroes the
+//                  accumulator it has read, so the reduce-add target is clean for the next use.
+// Reference semantics: FMT.py:151-198 (block / decoder), :277-340 (forward), :342-401 (CFG), torchdiffeq fixed-grid solvers.
+#pragma once
+#include "kernels.cuh"
+
+namespace fmt {
+
+constexpr int WIN_THREADS = 288;                 // warp 0: weight producer; warps 1..8: main group (256 threads)
+constexpr int WIN_MAIN = 256;
+constexpr int WIN_NW = 5;                        // weight ring slots
+constexpr int WIN_W_BYTES = 128 * 64 * 2;        // one weight tile: 128 features x 64 K, bf16
+constexpr int WIN_A_RING = 96 * 1024;            // activation ring: floor(96 KB / (Rp * 128 B)) slots
+constexpr int WIN_MAX_NA = 8;
+constexpr int WIN_STG_BYTES = 32 * 128 * 4;      // epilogue staging: 32 rows x 128 features fp32
+constexpr int WIN_BAR_BYTES = 512;
+constexpr int WIN_SMEM_BYTES = WIN_NW * WIN_W_BYTES + WIN_A_RING + 2 * WIN_STG_BYTES + WIN_BAR_BYTES + 1024;
+constexpr int WIN_MAX_DEPTH = 16;
+constexpr int WIN_MAX_GEMMS = 2 + 4 * WIN_MAX_DEPTH;
+
+struct WinGemm {
+  int tm_w, tm_a, tm_acc;   // tensor-map indices: weights (box 64 x 128), activations (box 64 x Rp), accumulator (box 128 x 32, fp32)
+  int n_ft;                 // ceil(N / 128) feature tiles
+  int nkb;                  // ceil(K / 64) K blocks
+  int pk;                   // K splits; n_ft * pk <= gridDim.x items, item i runs on CTA (i + cta_off) % gridDim.x
+  int cta_off;
+  int pad;
+};
+
+struct WinParams {
+  ModelShape s;
+  int R, Rp, depth, heads, window, mlp_hidden, NT;
+  int n_steps, n_stages, n_gemms;
+  WinGemm gemms[WIN_MAX_GEMMS];        // x_emb, (qkv, proj, fc1, fc2) x depth, dec
+  const CUtensorMap* tmaps;            // device array
+  float *X, *Pacc, *QKVacc, *Hacc, *Vacc;
+  __nv_bfloat16 *A1, *A2, *Hm, *ax;
+  const __nv_bfloat16* table;          // (n_eval, R, NT)
+  const float *b_x, *pos, *b_dec;
+  const float *b_qkv[WIN_MAX_DEPTH], *b_proj[WIN_MAX_DEPTH], *b_fc1[WIN_MAX_DEPTH], *b_fc2[WIN_MAX_DEPTH];
+  float *x_state, *kbuf;
+  const float* ddt;
+  float rk_a[16], rk_b[4];
+  const WindowArgs* wargs;
+  unsigned* bar_counter;               // zeroed before every launch
+  int* err_flag;
+  long long* trace;                    // optional (FMT_WIN_TRACE=1): [cta][barrier][6] SM-clock stamps (arrive, pass, 4 intra-stage marks of the NEXT stage)
+  int trace_stride;                    // barriers per CTA recorded
+  int w_lookahead;                     // weight prefetch may run this many stages ahead of the stage in flight (>= 1000: ungated)
+};
+
+// ---------------------------------------------------------------- small PTX helpers local to this kernel
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;" ::: "memory"); }   // measured: 100 cycles vs 590 for the all-space form
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int32_t crd0, int32_t crd1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Bounded spins: a protocol bug must end in a trap (reported as a launch failure), never in a hung GPU.
+constexpr long long WIN_SPIN_LIMIT = 4000000000ll;   // ~2 s of SM clocks
+__device__ __forceinline__ void win_fail(int* err_flag, int code) {
+  if (err_flag != nullptr) atomicExch(err_flag, code);
+  __threadfence_system();
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > WIN_SPIN_LIMIT) win_fail(err_flag, code);
+  }
+}
+
+// intra-stage mark `slot` (0..3) of the stage that follows barrier `epoch` (call from ONE thread per CTA and slot)
+__device__ __forceinline__ void win_mark(const WinParams& p, unsigned epoch, int slot) {
+  if (p.trace != nullptr && epoch >= 1 && static_cast<int>(epoch) <= p.trace_stride)
+    p.trace[(static_cast<size_t>(blockIdx.x) * p.trace_stride + (epoch - 1)) * 6 + 2 + slot] = clock64();
+}
+
+struct WinSmem {
+  uint8_t* wring;
+  uint8_t* aring;
+  float* stg;
+  uint64_t *w_full, *w_empty, *a_full, *a_empty, *t_full;
+  uint32_t* tmem_slot;
+  int* gate;          // quiet points passed (see win_weight_producer)
+};
+
+// grid barrier for the main group (256 threads, named barrier 1); `epoch` counts barriers passed
+__device__ __forceinline__ void win_grid_sync(const WinParams& p, unsigned& epoch) {
+  fence_proxy_async_all();                 // this thread's generic-proxy writes -> visible to later TMA (async proxy) reads
+  named_bar_sync(1, WIN_MAIN);
+  ++epoch;
+  if (threadIdx.x == 32) {
+    long long* tr = (p.trace != nullptr && static_cast<int>(epoch) <= p.trace_stride)
+                        ? p.trace + (static_cast<size_t>(blockIdx.x) * p.trace_stride + (epoch - 1)) * 6 : nullptr;
+    if (tr) tr[0] = clock64();
+    red_release_gpu_add(p.bar_counter, 1u);
+    const unsigned target = epoch * gridDim.x;
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(p.bar_counter) < target) {
+      if (clock64() - t0 > WIN_SPIN_LIMIT) win_fail(p.err_flag, 100 + static_cast<int>(epoch & 0xffff));
+    }
+    if (tr) tr[1] = clock64();
+  }
+  named_bar_sync(1, WIN_MAIN);
+}
+
+__device__ __forceinline__ bool win_item(const WinGemm& G, int& ft, int& kb0, int& kb1) {
+  int item = static_cast<int>(blockIdx.x) - G.cta_off;
+  if (item < 0) item += gridDim.x;
+  if (item >= G.n_ft * G.pk) return false;
+  ft = item % G.n_ft;
+  const int ks = item / G.n_ft;
+  kb0 = ks * G.nkb / G.pk;
+  kb1 = (ks + 1) * G.nkb / G.pk;
+  return kb1 > kb0;
+}
+
+struct WinRing {   // ring position kept identically by every lane of a role warp
+  int w_slot = 0; uint32_t w_phase = 0;
+  int a_slot = 0; uint32_t a_phase = 0;
+  uint32_t t_phase = 0;
+};
+
+// ---------------------------------------------------------------------------------------------------------------- GEMM
+__device__ __forceinline__ void win_gemm_stage(const WinParams& p, const WinGemm& G, const WinSmem& sm, WinRing& rg, int NA,
+                                               uint32_t tmem_base, unsigned epoch) {
+  int ft, kb0, kb1;
+  if (!win_item(G, ft, kb0, kb1)) {
+    if (threadIdx.x == 32) atomicAdd(sm.gate, 1);
+    return;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, mw = warp - 1;
+  const int a_bytes = p.Rp * 128;
+  if (mw == 0) {
+    // ===================== activation producer =====================
+    for (int kb = kb0; kb < kb1; ++kb) {
+      if (lane == 0) {
+        mbar_wait_b(&sm.a_empty[rg.a_slot], rg.a_phase ^ 1, p.err_flag, 1);
+        mbar_expect_tx(&sm.a_full[rg.a_slot], a_bytes);
+        tma_load_2d(&p.tmaps[G.tm_a], &sm.a_full[rg.a_slot], sm.aring + rg.a_slot * a_bytes, kb * 64, 0, kEvictLast);
+      }
+      if (++rg.a_slot == NA) { rg.a_slot = 0; rg.a_phase ^= 1; }
+    }
+    __syncwarp();
+  } else if (mw == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_bf16_f32(128, static_cast<uint32_t>(p.Rp));
+    for (int kb = kb0; kb < kb1; ++kb) {
+      if (lane == 0) {
+        mbar_wait_b(&sm.w_full[rg.w_slot], rg.w_phase, p.err_flag, 2);
+        mbar_wait_b(&sm.a_full[rg.a_slot], rg.a_phase, p.err_flag, 3);
+        if (kb == kb1 - 1) { atomicAdd(sm.gate, 1); win_mark(p, epoch, 0); }   // quiet point: this stage's operands have landed
+        tc_fence_after();
+        const uint64_t dw = make_sw128_kmajor_desc(smem_u32(sm.wring + rg.w_slot * WIN_W_BYTES));
+        const uint64_t da = make_sw128_kmajor_desc(smem_u32(sm.aring + rg.a_slot * a_bytes));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, dw + 2 * k, da + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        umma_commit(&sm.w_empty[rg.w_slot]);
+        umma_commit(&sm.a_empty[rg.a_slot]);
+        if (kb == kb1 - 1) umma_commit(sm.t_full);
+      }
+      if (++rg.w_slot == WIN_NW) { rg.w_slot = 0; rg.w_phase ^= 1; }
+      if (++rg.a_slot == NA) { rg.a_slot = 0; rg.a_phase ^= 1; }
+    }
+    __syncwarp();
+  } else if (mw >= 4) {
+    // ===================== epilogue: TMEM (lanes = features, columns = rows) -> smem [row][feature] -> TMA reduce-add
+    const int quarter = warp & 3;
+    const int fl = quarter * 32 + lane;
+    const bool issuer = (mw == 4 && lane == 0);
+    mbar_wait_b(sm.t_full, rg.t_phase, p.err_flag, 4);
+    rg.t_phase ^= 1;
+    tc_fence_after();
+    if (issuer) win_mark(p, epoch, 1);
+    const int n_chunks = (p.R + 31) / 32;
+    for (int c = 0; c < n_chunks; ++c) {
+      float* stg = sm.stg + (c & 1) * (WIN_STG_BYTES / 4);
+      float v[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, v);
+      if (c >= 2) {                       // the reduce that read this staging buffer two chunks ago must be done reading
+        if (issuer) bulk_wait_read<1>();
+        named_bar_sync(2, 128);
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) stg[j * 128 + fl] = v[j];
+      fence_proxy_async();                // smem writes -> visible to the async proxy
+      named_bar_sync(2, 128);
+      if (issuer) {
+        tma_reduce_add_2d(&p.tmaps[G.tm_acc], stg, ft * 128, c * 32);
+        bulk_commit();
+      }
+    }
+    if (issuer) {
+      win_mark(p, epoch, 2);
+      bulk_wait<0>();                     // all partial sums are in L2 before this CTA arrives at the grid barrier
+      win_mark(p, epoch, 3);
+    }
+    tc_fence_before();
+  }
+}
+
+// W-producer's view of the same item list (warp 0, free-running over the whole window)
+// Gating: the refill of the ring competes with the latency-critical loads of the stage in flight (measured: a SIMT stage's
+// L2 loads take 1.5 us instead of 0.65 us while 148 producers burst), so the weights of global stage s may only be
+// requested once `gate` (quiet points passed = stages whose own loads have landed) has reached s - w_lookahead + 1.
+__device__ __noinline__ void win_weight_producer(const WinParams& p, const WinSmem& sm, int n_eval) {
+  int slot = 0; uint32_t phase = 0;
+  const int spe = 4 + 8 * p.depth;                     // stages per evaluation
+  for (int e = 0; e < n_eval; ++e) {
+    for (int g = 0; g < p.n_gemms; ++g) {
+      const WinGemm& G = p.gemms[g];
+      int ft, kb0, kb1;
+      if (!win_item(G, ft, kb0, kb1)) continue;
+      const int si = g == 0 ? 0 : (g == p.n_gemms - 1 ? spe - 2 : 2 + 8 * ((g - 1) / 4) + 2 * ((g - 1) % 4));
+      const int need = e * spe + si - p.w_lookahead + 1;
+      if (need > 0) {
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile int*>(sm.gate) < need) {
+          __nanosleep(64);
+          if (clock64() - t0 > WIN_SPIN_LIMIT) win_fail(p.err_flag, 6);
+        }
+      }
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait_b(&sm.w_empty[slot], phase ^ 1, p.err_flag, 5);
+        mbar_expect_tx(&sm.w_full[slot], WIN_W_BYTES);
+        tma_load_2d(&p.tmaps[G.tm_w], &sm.w_full[slot], sm.wring + slot * WIN_W_BYTES, kb * 64, ft * 128, kEvictFirst);
+        if (++slot == WIN_NW) { slot = 0; phase ^= 1; }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- SIMT
+// Every SIMT stage is latency-bound (one L2 round trip is ~0.8 us, a stage has microseconds): all global loads of a work
+// item are issued before the first dependent instruction, and nothing is stored before the last load has been issued.
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void bf16x4_to_f32(uint2 t, float (&v)[4]) {
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x), b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+  v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+}
+__device__ __forceinline__ uint2 f32x4_to_bf16(const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 t;
+  t.x = *reinterpret_cast<uint32_t*>(&a);
+  t.y = *reinterpret_cast<uint32_t*>(&b);
+  return t;
+}
+__device__ __forceinline__ uint2 ld_nc_u2(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+
+// ROW stage.  WPR warps share one token row (FPL float4 per lane each); rows are dealt round-robin to CTAs.
+//   mode 0 (after x_embedder): X = acc + bias + pos_embed[frame]                       (FMT.py:319-320)
+//   mode 1 (after proj / fc2): X = X + gate * (acc + bias)                             (FMT.py:174-175)
+// then A1 = bf16( LayerNorm(X) * (1 + scale) + shift )  with this evaluation's table row  (FMT.py:168-169,174-175,197)
+// and the accumulator row (plus, after proj, the QKV accumulator row) is zeroed for its next use.
+template <int NV>
+__device__ __noinline__ void win_row_stage(const WinParams& p, float* red_smem, const __nv_bfloat16* __restrict__ table_e, int mode,
+                                              const float* __restrict__ bias, long long gate_off, long long shift_off, long long scale_off,
+                                              bool zero_qkv) {
+  constexpr int WPR = NV >= 4 ? 4 : NV;          // warps per row
+  constexpr int FPL = NV / WPR;                  // float4 per lane
+  constexpr int GROUPS = 8 / WPR;                // rows in flight per CTA
+  const int lane = threadIdx.x & 31, mw = (threadIdx.x >> 5) - 1;
+  const int grp = mw / WPR, wq = mw % WPR;
+  const int H = p.s.H;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = blockIdx.x + gridDim.x * grp; r < p.R; r += gridDim.x * GROUPS) {
+    const int c0 = wq * (FPL * 128) + lane * 4;                       // first column of this lane; + i*128 per float4
+    float* acc = p.Pacc + static_cast<size_t>(r) * H + c0;
+    float* xr = p.X + static_cast<size_t>(r) * H + c0;
+    const __nv_bfloat16* trow = table_e + static_cast<size_t>(r) * p.NT + c0;
+    float4 a[FPL], x[FPL], b[FPL], ps[FPL];
+    uint2 tg[FPL], tsh[FPL], tsc[FPL];
+#pragma unroll
+    for (int i = 0; i < FPL; ++i) {
+      a[i] = ldcg4(acc + i * 128);
+      tsh[i] = ld_nc_u2(trow + shift_off + i * 128);
+      tsc[i] = ld_nc_u2(trow + scale_off + i * 128);
+      b[i] = __ldg(reinterpret_cast<const float4*>(bias + c0 + i * 128));
+      if (mode == 1) {
+        x[i] = ldcg4(xr + i * 128);
+        tg[i] = ld_nc_u2(trow + gate_off + i * 128);
+      } else {
+        ps[i] = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(r % p.s.N) * H + c0 + i * 128));
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < FPL; ++i) {
+      if (mode == 0) {
+        x[i] = make_float4(a[i].x + b[i].x + ps[i].x, a[i].y + b[i].y + ps[i].y, a[i].z + b[i].z + ps[i].z, a[i].w + b[i].w + ps[i].w);
+      } else {
+        float g[4];
+        bf16x4_to_f32(tg[i], g);
+        x[i].x = fmaf(g[0], a[i].x + b[i].x, x[i].x); x[i].y = fmaf(g[1], a[i].y + b[i].y, x[i].y);
+        x[i].z = fmaf(g[2], a[i].z + b[i].z, x[i].z); x[i].w = fmaf(g[3], a[i].w + b[i].w, x[i].w);
+      }
+      sum += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+    }
+#pragma unroll
+    for (int i = 0; i < FPL; ++i) {
+      *reinterpret_cast<float4*>(xr + i * 128) = x[i];
+      *reinterpret_cast<float4*>(acc + i * 128) = zero4;
+    }
+    if (zero_qkv) {
+      float* q = p.QKVacc + static_cast<size_t>(r) * 3 * H + wq * (3 * FPL * 128) + lane * 4;
+#pragma unroll
+      for (int i = 0; i < 3 * FPL; ++i) *reinterpret_cast<float4*>(q + i * 128) = zero4;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (WPR > 1) {
+      if (lane == 0) red_smem[mw] = sum;
+      named_bar_sync(3 + grp, WPR * 32);
+      sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < WPR; ++w) sum += red_smem[grp * WPR + w];
+    }
+    const float mean = sum / static_cast<float>(H);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < FPL; ++i) {
+      const float d0 = x[i].x - mean, d1 = x[i].y - mean, d2 = x[i].z - mean, d3 = x[i].w - mean;
+      var += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    if (WPR > 1) {
+      if (lane == 0) red_smem[8 + mw] = var;
+      named_bar_sync(3 + grp, WPR * 32);
+      var = 0.f;
+#pragma unroll
+      for (int w = 0; w < WPR; ++w) var += red_smem[8 + grp * WPR + w];
+    }
+    const float rstd = rsqrtf(var / static_cast<float>(H) + 1e-6f);
+#pragma unroll
+    for (int i = 0; i < FPL; ++i) {
+      float sh[4], sc[4];
+      bf16x4_to_f32(tsh[i], sh);
+      bf16x4_to_f32(tsc[i], sc);
+      float v[4] = {(x[i].x - mean) * rstd, (x[i].y - mean) * rstd, (x[i].z - mean) * rstd, (x[i].w - mean) * rstd};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = fmaf(v[k], 1.f + sc[k], sh[k]);
+      *reinterpret_cast<uint2*>(p.A1 + static_cast<size_t>(r) * H + c0 + i * 128) = f32x4_to_bf16(v);
+    }
+    if (WPR > 1) named_bar_sync(3 + grp, WPR * 32);   // red_smem is reused by the next row of this group
+  }
+}
+
+// ATTN stage: band-masked attention (FMT.py:15-19,69-88) straight from the fp32 QKV accumulator (+ qkv bias); one warp
+// per (sequence, head, query row), TWO units interleaved per warp so their loads are in flight together.
+// Output A2 bf16 = operand of the proj GEMM.
+template <int VPL> struct F32Vec;
+template <> struct F32Vec<1> { static __device__ __forceinline__ void ld(const float* p, float (&v)[1]) { v[0] = __ldcg(p); } };
+template <> struct F32Vec<2> { static __device__ __forceinline__ void ld(const float* p, float (&v)[2]) { float2 t = __ldcg(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y; } };
+template <> struct F32Vec<4> { static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) { float4 t = __ldcg(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; } };
+
+// Fast path (band of at most 5 keys = attention_window <= 2): U units per warp, all loads first, plain (not online) softmax.
+template <int VPL, int U /* units interleaved per warp */>
+__device__ __noinline__ void win_attn_band5(const WinParams& p, const float* __restrict__ bqkv) {
+  const int lane = threadIdx.x & 31, mw = (threadIdx.x >> 5) - 1;
+  constexpr int hd = VPL * 32, KB = 5;
+  const int N = p.s.N, heads = p.heads, H = p.s.H, ld = 3 * H;
+  const int n_units = p.R * heads;
+  const float scale = rsqrtf(static_cast<float>(hd));
+  const int win = p.window;
+  const int stride = gridDim.x * 8;
+#pragma unroll 1
+  for (int u0 = blockIdx.x + gridDim.x * mw; u0 < n_units; u0 += U * stride) {
+    int row[U], hh[U], j0[U], nk[U];
+    bool valid[U];
+    float q[U][VPL], kv[U][KB][VPL], vv[U][KB][VPL];
+#pragma unroll
+    for (int t = 0; t < U; ++t) {
+      const int u = u0 + t * stride;
+      valid[t] = u < n_units;
+      const int uu = valid[t] ? u : u0;
+      hh[t] = uu % heads; row[t] = uu / heads;
+      const int fi = row[t] % N, sq = row[t] / N;
+      const float* base = p.QKVacc + static_cast<size_t>(sq) * N * ld + hh[t] * hd + lane * VPL;
+      j0[t] = max(0, fi - win);
+      const int j1 = min(N - 1, fi + win);
+      nk[t] = j1 - j0[t] + 1;
+      F32Vec<VPL>::ld(base + static_cast<size_t>(fi) * ld, q[t]);
+#pragma unroll
+      for (int k = 0; k < KB; ++k) {
+        const int j = min(j0[t] + k, j1);
+        F32Vec<VPL>::ld(base + static_cast<size_t>(j) * ld + H, kv[t][k]);
+        F32Vec<VPL>::ld(base + static_cast<size_t>(j) * ld + 2 * H, vv[t][k]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < U; ++t) {
+      const float* bq = bqkv + hh[t] * hd + lane * VPL;
+      float s[KB];
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) q[t][k] += __ldg(bq + k);
+#pragma unroll
+      for (int c = 0; c < KB; ++c) {
+        float d = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) d = fmaf(q[t][k], kv[t][c][k] + __ldg(bq + H + k), d);
+        s[c] = d;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int c = 0; c < KB; ++c) s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < KB; ++c) { s[c] = c < nk[t] ? s[c] * scale : -INFINITY; mx = fmaxf(mx, s[c]); }
+      float den = 0.f, acc[VPL];
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) acc[k] = 0.f;
+#pragma unroll
+      for (int c = 0; c < KB; ++c) {
+        const float pr = __expf(s[c] - mx);          // exp(-inf) = 0 for the masked slots
+        den += pr;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) acc[k] = fmaf(pr, vv[t][c][k], acc[k]);
+      }
+      if (valid[t]) {
+        const float inv = __fdividef(1.f, den);
+        __nv_bfloat16* op = p.A2 + static_cast<size_t>(row[t]) * H + hh[t] * hd + lane * VPL;
+        float o[VPL];
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) o[k] = fmaf(acc[k], inv, __ldg(bq + 2 * H + k));   // sum_c p_c (v_c + b) / den = sum_c p_c v_c / den + b
+        if constexpr (VPL == 4) {
+          *reinterpret_cast<uint2*>(op) = f32x4_to_bf16(o);
+        } else {
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) op[k] = __float2bfloat16_rn(o[k]);
+        }
+      }
+    }
+  }
+}
+
+// General band width: one unit per warp, keys in batches of 4 with an online softmax (compact code; rarely used).
+template <int VPL>
+__device__ __noinline__ void win_attn_wide(const WinParams& p, const float* __restrict__ bqkv) {
+  const int lane = threadIdx.x & 31, mw = (threadIdx.x >> 5) - 1;
+  constexpr int hd = VPL * 32, KB = 4;
+  const int N = p.s.N, heads = p.heads, H = p.s.H, ld = 3 * H;
+  const int n_units = p.R * heads;
+  const float scale = rsqrtf(static_cast<float>(hd));
+  const int win = p.window;
+#pragma unroll 1
+  for (int u = blockIdx.x + gridDim.x * mw; u < n_units; u += gridDim.x * 8) {
+    const int h = u % heads, row = u / heads, fi = row % N, sq = row / N;
+    const float* base = p.QKVacc + static_cast<size_t>(sq) * N * ld + h * hd + lane * VPL;
+    const float* bq = bqkv + h * hd + lane * VPL;
+    float q[VPL], bk[VPL];
+    F32Vec<VPL>::ld(base + static_cast<size_t>(fi) * ld, q);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) { q[k] += __ldg(bq + k); bk[k] = __ldg(bq + H + k); }
+    const int j0 = max(0, fi - win), j1 = min(N - 1, fi + win);
+    float mx = -INFINITY, den = 0.f, acc[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) acc[k] = 0.f;
+#pragma unroll 1
+    for (int jb = j0; jb <= j1; jb += KB) {
+      float kv[KB][VPL], vv[KB][VPL], s[KB];
+#pragma unroll
+      for (int c = 0; c < KB; ++c) {
+        const int j = min(jb + c, j1);
+        F32Vec<VPL>::ld(base + static_cast<size_t>(j) * ld + H, kv[c]);
+        F32Vec<VPL>::ld(base + static_cast<size_t>(j) * ld + 2 * H, vv[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < KB; ++c) {
+        float d = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) d = fmaf(q[k], kv[c][k] + bk[k], d);
+        s[c] = d;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int c = 0; c < KB; ++c) s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+#pragma unroll
+      for (int c = 0; c < KB; ++c) {
+        if (jb + c <= j1) {
+          const float sc = s[c] * scale;
+          const float nmx = fmaxf(mx, sc);
+          const float corr = __expf(mx - nmx), pr = __expf(sc - nmx);
+          den = den * corr + pr;
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) acc[k] = fmaf(acc[k], corr, pr * vv[c][k]);
+          mx = nmx;
+        }
+      }
+    }
+    const float inv = __fdividef(1.f, den);
+    __nv_bfloat16* op = p.A2 + static_cast<size_t>(row) * H + h * hd + lane * VPL;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) op[k] = __float2bfloat16_rn(fmaf(acc[k], inv, __ldg(bq + 2 * H + k)));
+  }
+}
+
+// GELU stage: Hm = bf16( GELU_tanh(Hacc + b_fc1) ), Hacc <- 0      (timm Mlp: fc1 -> act, FMT.py:159-162)
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u = k0 * (x + k1 * x * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * (1.0f + t);
+}
+__device__ __noinline__ void win_gelu_stage(const WinParams& p, const float* __restrict__ b1, unsigned epoch) {
+  const int M4 = p.mlp_hidden;
+  const unsigned total4 = static_cast<unsigned>(p.R) * M4 / 4;
+  const unsigned stride = gridDim.x * WIN_MAIN;
+  constexpr int NB = 6;                                  // float4 per thread per batch (R = 180, 4096 hidden: 5 per thread)
+  for (unsigned i0 = blockIdx.x * WIN_MAIN + (threadIdx.x - 32); i0 < total4; i0 += NB * stride) {
+    float4 a[NB], b[NB];
+    win_mark(p, epoch, 0);
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      const unsigned i = i0 + k * stride;
+      if (i < total4) {
+        a[k] = ldcg4(p.Hacc + static_cast<size_t>(i) * 4);
+        b[k] = __ldg(reinterpret_cast<const float4*>(b1 + (i * 4) % static_cast<unsigned>(M4)));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      const unsigned i = i0 + k * stride;
+      if (i < total4) {
+        if (k == 0) win_mark(p, epoch, 1);
+        float v[4] = {gelu_tanh_fast(a[k].x + b[k].x), gelu_tanh_fast(a[k].y + b[k].y), gelu_tanh_fast(a[k].z + b[k].z), gelu_tanh_fast(a[k].w + b[k].w)};
+        *reinterpret_cast<uint2*>(p.Hm + static_cast<size_t>(i) * 4) = f32x4_to_bf16(v);
+        *reinterpret_cast<float4*>(p.Hacc + static_cast<size_t>(i) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    win_mark(p, epoch, 2);
+  }
+  win_mark(p, epoch, 3);
+}
+
+// COMB stage: decoder bias, CFG combine (FMT.py:375-379,396-399), then the explicit Runge-Kutta bookkeeping of stage g of
+// step `step` (Euler: y += dt * v).  Writes the x-embedder operand `ax` of the next evaluation and zeroes Vacc.
+__device__ __noinline__ void win_comb_stage(const WinParams& p, int step, int g) {
+  const ModelShape& s = p.s;
+  const int G = p.n_stages;
+  const size_t per_branch = static_cast<size_t>(s.B) * s.N * s.W;
+  const size_t nx = static_cast<size_t>(s.B) * s.L * s.W;
+  for (unsigned i = blockIdx.x * WIN_MAIN + (threadIdx.x - 32); i < per_branch; i += gridDim.x * WIN_MAIN) {   // R <= 256 rows: 32-bit indices
+    const int j = static_cast<int>(i % static_cast<unsigned>(s.W));
+    const int f = static_cast<int>((i / static_cast<unsigned>(s.W)) % static_cast<unsigned>(s.N)), b = static_cast<int>(i / static_cast<unsigned>(s.W * s.N));
+    const bool cur = f >= s.P;
+    const size_t o = cur ? (static_cast<size_t>(b) * s.L + (f - s.P)) * s.W + j : 0;
+    // ---- every load of this element first
+    float vb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int br = 0; br < 4; ++br)
+      if (br < s.nb) vb[br] = __ldcg(p.Vacc + br * per_branch + i);
+    const float bd = __ldg(p.b_dec + j);
+    const float dt = __ldg(p.ddt + step);
+    const float a_s = __ldg(&p.wargs->a_scale), r_s = __ldg(&p.wargs->r_scale), e_s = __ldg(&p.wargs->e_scale);
+    const float y0 = cur ? __ldcg(p.x_state + o) : 0.f;
+    float kprev[4] = {0.f, 0.f, 0.f, 0.f};
+    if (G > 1 && cur) {
+#pragma unroll
+      for (int jj = 0; jj < 3; ++jj)
+        if (jj < g) kprev[jj] = __ldcg(p.kbuf + static_cast<size_t>(jj) * nx + o);
+    }
+    // ---- then the arithmetic and the stores
+#pragma unroll
+    for (int br = 0; br < 4; ++br)
+      if (br < s.nb) { vb[br] += bd; p.Vacc[br * per_branch + i] = 0.f; }
+    if (!cur) continue;
+    float v;
+    if (s.nb == 1) v = vb[0];
+    else if (s.nb == 3) v = vb[0] + a_s * (vb[2] - vb[0]) + e_s * (vb[1] - vb[2]);
+    else v = vb[0] + r_s * (vb[1] - vb[0]) + a_s * (vb[3] - vb[1]) + e_s * (vb[2] - vb[3]);
+    float y;
+    if (G == 1) {
+      y = fmaf(dt, v, y0);
+      p.x_state[o] = y;
+    } else {
+      p.kbuf[static_cast<size_t>(g) * nx + o] = v;
+      const bool last = (g == G - 1);
+      const float* c = last ? p.rk_b : &p.rk_a[(g + 1) * G];
+      float acc = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+        if (jj <= g && c[jj] != 0.f) acc = fmaf(c[jj], jj == g ? v : kprev[jj], acc);
+      y = fmaf(dt, acc, y0);
+      if (last) p.x_state[o] = y;
+    }
+    const __nv_bfloat16 t = __float2bfloat16_rn(y);
+    for (int br = 0; br < s.nb; ++br) p.ax[((static_cast<size_t>(br) * s.B + b) * s.N + f) * s.W + j] = t;
+  }
+}
+
+__device__ __forceinline__ void win_attn_dispatch(const WinParams& p, const float* bqkv) {
+  const int hd = p.s.H / p.heads;
+  if (p.window <= 2) {
+    if (hd == 128) win_attn_band5<4, 2>(p, bqkv);
+    else if (hd == 64) win_attn_band5<2, 2>(p, bqkv);
+    else win_attn_band5<1, 2>(p, bqkv);
+  } else {
+    if (hd == 128) win_attn_wide<4>(p, bqkv);
+    else if (hd == 64) win_attn_wide<2>(p, bqkv);
+    else win_attn_wide<1>(p, bqkv);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- kernel
+template <int NV /* dim_h / 128 */>
+__global__ void __launch_bounds__(WIN_THREADS, 1) fmt_window_kernel(const WinParams* __restrict__ pp) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ WinParams p;
+  __shared__ float red_smem[16];
+  {
+    const int4* src = reinterpret_cast<const int4*>(pp);
+    int4* dst = reinterpret_cast<int4*>(&p);
+    for (int i = threadIdx.x; i < static_cast<int>(sizeof(WinParams) / 16); i += WIN_THREADS) dst[i] = src[i];
+  }
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  WinSmem sm;
+  sm.wring = smem;
+  sm.aring = smem + WIN_NW * WIN_W_BYTES;
+  sm.stg = reinterpret_cast<float*>(sm.aring + WIN_A_RING);
+  sm.w_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm.stg) + 2 * WIN_STG_BYTES);
+  sm.w_empty = sm.w_full + WIN_NW;
+  sm.a_full = sm.w_empty + WIN_NW;
+  sm.a_empty = sm.a_full + WIN_MAX_NA;
+  sm.t_full = sm.a_empty + WIN_MAX_NA;
+  sm.tmem_slot = reinterpret_cast<uint32_t*>(sm.t_full + 1);
+  sm.gate = reinterpret_cast<int*>(sm.tmem_slot + 1);
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int NA = WIN_A_RING / (p.Rp * 128);
+  if (NA > WIN_MAX_NA) NA = WIN_MAX_NA;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < WIN_NW; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
+    for (int i = 0; i < WIN_MAX_NA; ++i) { mbar_init(&sm.a_full[i], 1); mbar_init(&sm.a_empty[i], 1); }
+    mbar_init(sm.t_full, 1);
+    *sm.gate = 0;
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(sm.tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *sm.tmem_slot;
+  const int n_eval = p.n_steps * p.n_stages;
+
+  if (warp == 0) {
+    if (lane == 0) win_weight_producer(p, sm, n_eval);
+    __syncwarp();
+  } else {
+    // One call site per stage kind: the stage list of an evaluation is decoded from its index, so the GEMM stage (ring
+    // state in registers) is inlined exactly once and the hot code stays small.
+    //   0: x_embedder GEMM   1: ROW (init)   2 + 8*blk + {0: qkv GEMM, 1: ATTN, 2: proj GEMM, 3: ROW, 4: fc1 GEMM, 5: GELU,
+    //   6: fc2 GEMM, 7: ROW}   spe-2: decoder GEMM   spe-1: COMB
+    WinRing rg;
+    unsigned epoch = 0;
+    const int D = p.depth;
+    const int spe = 4 + 8 * D;
+    const size_t eval_stride = static_cast<size_t>(p.R) * p.NT;
+    const long long H = p.s.H;
+    for (int e = 0; e < n_eval; ++e) {
+      const __nv_bfloat16* table_e = p.table + static_cast<size_t>(e) * eval_stride;
+      for (int si = 0; si < spe; ++si) {
+        const int j = (si - 2) & 7, blk = (si - 2) >> 3;
+        const bool is_edge = si < 2 || si >= spe - 2;
+        const bool is_gemm = is_edge ? (si == 0 || si == spe - 2) : ((j & 1) == 0);
+        if (is_gemm) {
+          const int g = si == 0 ? 0 : (si == spe - 2 ? 1 + 4 * D : 1 + 4 * blk + (j >> 1));
+          win_gemm_stage(p, p.gemms[g], sm, rg, NA, tmem_base, epoch);
+        } else {
+          if (si == spe - 1) {
+            win_comb_stage(p, e / p.n_stages, e % p.n_stages);
+          } else if (si == 1) {
+            win_row_stage<NV>(p, red_smem, table_e, 0, p.b_x, 0, 0, H, false);      // LN + modulate with block 0's (shift_msa, scale_msa)
+          } else if (j == 1) {
+            win_attn_dispatch(p, p.b_qkv[blk]);
+          } else if (j == 5) {
+            win_gelu_stage(p, p.b_fc1[blk], epoch);
+          } else {
+            const long long base = static_cast<long long>(blk) * 6 * H;
+            // j == 3: after proj -> gate_msa, then the mlp modulation; j == 7: after fc2 -> gate_mlp, then the NEXT block's msa
+            // modulation or, after the last block, the decoder's (shift, scale)
+            const bool after_proj = (j == 3);
+            const long long gate_off = base + (after_proj ? 2 : 5) * H;
+            const long long mod = after_proj ? base + 3 * H : base + 6 * H;
+            win_row_stage<NV>(p, red_smem, table_e, 1, after_proj ? p.b_proj[blk] : p.b_fc2[blk], gate_off, mod, mod + H, after_proj);
+          }
+          if (threadIdx.x == 32) atomicAdd(sm.gate, 1);                             // quiet point of a SIMT stage: its loads have landed
+        }
+        win_grid_sync(p, epoch);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace fmt

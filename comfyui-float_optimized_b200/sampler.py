@@ -176,6 +176,10 @@ class FmtBackend:
     def launch_count(self, reset: bool = False) -> int:
         return int(self.lib.fmt_launch_count(self._handle, int(reset)))
 
+    def window_kernel_status(self) -> int:
+        """-1: the current plan runs one kernel per op; 0: the persistent window kernel is in use; >0: it trapped."""
+        return int(self.lib.fmt_window_kernel_status(self._handle))
+
     def graph_kernel_nodes(self) -> int:
         return int(self.lib.fmt_graph_kernel_nodes(self._handle))
 

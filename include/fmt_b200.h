@@ -157,6 +157,14 @@ FMT_API int64_t fmt_launch_count(const FmtHandle* h, int32_t reset);
 /* Number of kernel nodes in the captured window graph (0 before fmt_configure). */
 FMT_API int32_t fmt_graph_kernel_nodes(const FmtHandle* h);
 
+/* Persistent window kernel (plans with <= 256 token rows, bf16): -1 = not in use for the current plan, 0 = in use and
+ * healthy, > 0 = id of the bounded spin that tripped (the kernel traps instead of hanging the GPU). */
+FMT_API int32_t fmt_window_kernel_status(const FmtHandle* h);
+
+/* With FMT_WIN_TRACE=1 in the environment at fmt_configure: copies the per-CTA barrier stamps of the last window,
+ * [cta][barrier][arrive, pass] in SM clocks, into `out` (HOST); returns the element count (call with NULL to size). */
+FMT_API int64_t fmt_debug_window_trace(const FmtHandle* h, int64_t* out, int64_t max_elems);
+
 /* ---- diagnostic entry points (unit tests of the kernels; not used by the node) ---- */
 /* out[M,N] (fp32) = A[M,K] (bf16 bits) @ W[N,K]^T (bf16 bits) + bias[N], through the tcgen05/TMA GEMM. */
 FMT_API int32_t fmt_debug_gemm_bf16(const void* A, const void* W, const float* bias, float* out, int32_t M, int32_t N,

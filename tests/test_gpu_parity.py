@@ -189,3 +189,29 @@ def test_errors_mirror_reference(pkg):
     cpu_model = pkg.FmtModel(cases.weights("full"), target_device="cpu")
     with pytest.raises(pkg.FmtError):
         node.sample_rd_sequence_va(r_s, wa, we, 50, cpu_model, *args)
+
+
+@pytest.mark.parametrize("method,nfe,nb_scales", [("euler", 4, (2.0, 1.0, 1.0, False)), ("heun3", 3, (2.0, 1.0, 1.0, False)),
+                                                   ("euler", 3, (1.0, 1.0, 1.0, False)), ("midpoint", 3, (2.0, 0.5, 1.5, True))])
+def test_window_kernel_matches_per_op_path(pkg, monkeypatch, method, nfe, nb_scales):
+    """The persistent window kernel (<= 256 token rows) and the one-kernel-per-op path are two schedules of the same
+    arithmetic (bf16 operands, fp32 accumulation): same result up to bf16 rounding of intermediates."""
+    d = cases.FmtDims()
+    from oracle.synth import synth_inputs
+    a, r, e, inc = nb_scales
+    B, T = 1, 120
+    r_s, wa, we = [t.to(DEV) for t in synth_inputs(d, B, T, seed=21)]
+    g = torch.Generator().manual_seed(5)
+    noise = torch.stack([torch.randn(B, d.frames_per_clip, d.dim_w, generator=g) for _ in range(3)]).to(DEV)
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("FMT_WINDOW", flag)
+        be = pkg.FmtBackend(cases.weights("full"), pkg.Dims(), DEV)
+        be.configure(B, pkg.n_branches_for(a, r, e, inc), False, nfe, method, "bf16")
+        assert be.window_kernel_status() == (0 if flag == "1" else -1)
+        outs[flag] = be.sample_clip(r_s, wa, we, T, noise, a, r, e).cpu()
+        torch.cuda.synchronize()
+        assert be.window_kernel_status() == (0 if flag == "1" else -1)
+        be.close()
+    assert torch.isfinite(outs["1"]).all()
+    assert cases.max_abs(outs["1"], outs["0"]) <= 1e-2, cases.max_abs(outs["1"], outs["0"])
