@@ -67,6 +67,7 @@ _SIGNATURES = {
     "fmt_window_kernel_status": (C.c_int32, [C.c_void_p]),
     "fmt_debug_window_trace": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
     "fmt_debug_gemm_bf16": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "fmt_debug_gemm_bench": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "fmt_debug_gemm_fp32": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 

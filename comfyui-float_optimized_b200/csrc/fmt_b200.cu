@@ -85,6 +85,8 @@ struct FmtHandle {
   DevBuf cond, cemb, temb, tfreq, th, silu, table, xstate, ystage, kbuf, prevx, ax, X, A1, QKV, A2, Hm, V, ddt, dteval, wargs;
   DevBuf st_rs, st_wa, st_we, st_noise, st_rd;   // staging for host-located clips
   DevBuf sk_scratch, sk_counters;                // split-K fix-up state of the skinny GEMM (kept all-zero between launches)
+  int raster_gm = 8;                             // FMT_RASTER_GM
+  bool use_pair = true;                          // CTA-pair (cta_group::2) GEMM for M >= 512 (FMT_PAIR=0 disables)
   bool use_pdl = true;                           // programmatic dependent launch between graph nodes (FMT_PDL=0 disables)
   bool use_skinny = false;                       // atomic split-K skinny-M GEMM (FMT_SKINNY=1 enables; measured slower than the tiled path, kept for tests)
   int sk_cluster = 8;                            // cluster size of the skinny GEMM (FMT_SK_CLUSTER)
@@ -193,6 +195,26 @@ static int launch_tc(FmtHandle* h, const bf16* A, int lda, const bf16* W, int ld
   return launch(h, gemm_tc_kernel<BN, bf16>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, 1, ta, tb, ep, K);
 }
 
+template <int BN>
+static int launch_tc2(FmtHandle* h, const bf16* A, int lda, const bf16* W, int ldw, const EpiParams& ep, int K, cudaStream_t st) {
+  using C = Tc2Cfg<BN>;
+  static bool attr_set[64] = {};
+  if (!attr_set[h->device & 63]) {
+    CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<BN, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set[h->device & 63] = true;
+  }
+  CUtensorMap ta, tb;
+  FMT_OK(make_tmap(h, &ta, A, ep.M, K, lda, C::BMH));
+  FMT_OK(make_tmap(h, &tb, W, ep.N, K, ldw, BN / 2));
+  const int tiles = ((ep.M + C::BM - 1) / C::BM) * ((ep.N + BN - 1) / BN);
+  const int max_pairs = h->num_sms / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  EpiParams ep2 = ep;
+  ep2.raster_gm = h->raster_gm;
+  // the kernel carries __cluster_dims__(2,1,1); launch() only adds the PDL attribute
+  return launch(h, gemm_tc2_kernel<BN, bf16>, dim3(2 * pairs), dim3(C::THREADS), C::SMEM_BYTES, st, 1, ta, tb, ep2, K);
+}
+
 // ---- skinny-M path (weights as the UMMA M operand, all rows as N; see skinny.cuh)
 static int make_tmap_box(FmtHandle* h, CUtensorMap* m, const void* ptr, int rows, int cols, int ld_elems, int box_rows);
 
@@ -241,6 +263,22 @@ static int gemm_bf16(FmtHandle* h, const bf16* A, int lda, const bf16* W, int ld
   REQUIRE(ep.N % 32 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm_bf16: N %% 32, K/lda/ldw %% 8 required (N=%d K=%d)", ep.N, K);
   if (force_bn == -1 || (force_bn == 0 && h->use_skinny && ep.M <= 256 && ep.N % 128 == 0 && K % 64 == 0 && h->sk_scratch.p != nullptr))
     return gemm_skinny(h, A, lda, W, ldw, ep, K, st);
+  // CTA-pair kernel (force_bn 512 / 1024 = pair tiles 256x256 / 256x128): the default once there are enough 256-row tiles
+  if (force_bn == 512) return launch_tc2<256>(h, A, lda, W, ldw, ep, K, st);
+  if (force_bn == 1024) return launch_tc2<128>(h, A, lda, W, ldw, ep, K, st);
+  if (force_bn == 0 && h->use_pair && ep.M >= 512 && ep.N % 256 == 0 && K % 64 == 0) {
+    // Wave model calibrated on B200 (tools/gemm_bench.py): time ~ waves x per-wave cost.  A pair tile (256x256 on two SMs)
+    // and a single-CTA 128x256 tile cost the same per wave at 32 clips, but at >= 128 clips the pair kernel is 20 % cheaper
+    // (half the L2 -> SM operand traffic); a 128x128 tile costs 0.56 of a wave and wins when the wider tiles leave the last
+    // wave mostly empty (N = 1024 at 32 clips: 92 pair tiles on 74 pairs).
+    const int sms = h->num_sms, pairs = sms / 2, mt128 = (ep.M + 127) / 128, mt256 = (ep.M + 255) / 256;
+    const auto waves = [](int tiles, int units) { return static_cast<double>((tiles + units - 1) / units); };
+    const double c_pair = waves(mt256 * (ep.N / 256), pairs);
+    const double c_256 = waves(mt128 * (ep.N / 256), sms) * (ep.M >= 16384 ? 1.2 : 1.02);
+    const double c_128 = waves(mt128 * (ep.N / 128), sms) * 0.56;
+    if (c_pair <= c_256 && c_pair <= c_128) return launch_tc2<256>(h, A, lda, W, ldw, ep, K, st);
+    return c_128 < c_256 ? launch_tc<128>(h, A, lda, W, ldw, ep, K, st) : launch_tc<256>(h, A, lda, W, ldw, ep, K, st);
+  }
   const int bn = force_bn > 0 ? force_bn : pick_bn(h, ep.M, ep.N);
   switch (bn) {
     case 256: return launch_tc<256>(h, A, lda, W, ldw, ep, K, st);
@@ -325,6 +363,20 @@ static int launch_attn(FmtHandle* h, cudaStream_t st) {
   const T* qkv = static_cast<const T*>(h->QKV.p);
   T* out = static_cast<T*>(h->A2.p);
   const int win = h->d.attention_window;
+  if constexpr (sizeof(T) == 2) {
+    // many sequences: one CTA per (sequence, head) with K / V staged in shared memory (every qkv byte read once)
+    const size_t tile_smem = static_cast<size_t>(2) * s.N * hd * sizeof(bf16);
+    if (n_seq * heads >= 2 * h->num_sms && tile_smem <= 48 * 1024 && hd % 8 == 0) {
+      const bf16* q16 = reinterpret_cast<const bf16*>(qkv);
+      bf16* o16 = reinterpret_cast<bf16*>(out);
+      const dim3 tg(n_seq * heads), tb(128);
+      switch (hd) {
+        case 32: return launch(h, band_attention_tile_kernel<1>, tg, tb, tile_smem, st, 1, q16, s.N, heads, win, scale, o16);
+        case 64: return launch(h, band_attention_tile_kernel<2>, tg, tb, tile_smem, st, 1, q16, s.N, heads, win, scale, o16);
+        case 128: return launch(h, band_attention_tile_kernel<4>, tg, tb, tile_smem, st, 1, q16, s.N, heads, win, scale, o16);
+      }
+    }
+  }
   switch (hd) {
     case 32: return launch(h, band_attention_kernel<T, 1>, grid, block, 0, st, 1, qkv, n_seq, s.N, heads, win, scale, out);
     case 64: return launch(h, band_attention_kernel<T, 2>, grid, block, 0, st, 1, qkv, n_seq, s.N, heads, win, scale, out);
@@ -633,6 +685,8 @@ int32_t fmt_create(const FmtDims* dims, const void* const* wp, int32_t n_ptrs, i
   if (const char* e = getenv("FMT_PDL")) h->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("FMT_SKINNY")) h->use_skinny = atoi(e) != 0;
   if (const char* e = getenv("FMT_WINDOW")) h->use_window = atoi(e) != 0;
+  if (const char* e = getenv("FMT_PAIR")) h->use_pair = atoi(e) != 0;
+  if (const char* e = getenv("FMT_RASTER_GM")) { int v = atoi(e); if (v >= 1) h->raster_gm = v; }
   if (const char* e = getenv("FMT_WIN_PK")) sscanf(e, "%d,%d,%d,%d", &h->win_pk[0], &h->win_pk[1], &h->win_pk[2], &h->win_pk[3]);
   if (const char* e = getenv("FMT_SK_CLUSTER")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) h->sk_cluster = v; }
   if (const char* e = getenv("FMT_SK_CTAS")) { int v = atoi(e); if (v >= 1) h->sk_target_ctas = v; }
@@ -980,6 +1034,7 @@ int32_t fmt_debug_gemm_bf16(const void* A, const void* W, const float* bias, flo
   FmtHandle h;
   FMT_OK(debug_handle(h));
   h.use_pdl = false;
+  if (const char* e = getenv("FMT_RASTER_GM")) { int v = atoi(e); if (v >= 1) h.raster_gm = v; }
   if (const char* e = getenv("FMT_SK_CLUSTER")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) h.sk_cluster = v; }
   if (const char* e = getenv("FMT_SK_CTAS")) { int v = atoi(e); if (v >= 1) h.sk_target_ctas = v; }
   EpiParams ep = epi(EPI_STORE, M, N, bias, out, N, 1);
@@ -997,6 +1052,20 @@ int32_t fmt_debug_gemm_bf16(const void* A, const void* W, const float* bias, flo
     return rc;
   }
   return gemm_bf16(&h, static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), K, ep, K, st, block_n);
+}
+
+// `iters` back-to-back launches of one bf16 GEMM kernel variant through a single handle (kernel timing in isolation)
+int32_t fmt_debug_gemm_bench(const void* A, const void* W, const float* bias, float* out, int32_t M, int32_t N, int32_t K, int32_t block_n,
+                             int32_t iters, void* stream) {
+  static FmtHandle* hp = nullptr;       // device queries are slow: keep them out of the timed launches
+  if (!hp) { hp = new FmtHandle(); FMT_OK(debug_handle(*hp)); }
+  FmtHandle& h = *hp;
+  h.use_pdl = false;
+  if (const char* e = getenv("FMT_RASTER_GM")) { int v = atoi(e); if (v >= 1) h.raster_gm = v; }
+  EpiParams ep = epi(EPI_STORE, M, N, bias, out, N, 0);     // bf16 output, like the qkv / fc1 GEMMs of the step
+  for (int i = 0; i < iters; ++i)
+    FMT_OK(gemm_bf16(&h, static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), K, ep, K, static_cast<cudaStream_t>(stream), block_n));
+  return 0;
 }
 
 int32_t fmt_debug_gemm_fp32(const float* A, const float* W, const float* bias, float* out, int32_t M, int32_t N, int32_t K, void* stream) {

@@ -26,6 +26,7 @@ struct EpiParams {
   const int* urow;     // row indirection into the table (nullptr = identity)
   long long ldg;
   long long gate_off;
+  int raster_gm;       // CTA-pair kernel: row-tiles per raster group (>= 1)
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -38,6 +39,34 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// 256-bit global store (sm_100+): one full 32-byte L2 sector per lane.  The tcgen05 epilogues hold one output ROW per lane,
+// so a warp-wide store instruction touches 32 different lines; with 16-byte stores every sector was written in two halves
+// (partial-sector writes -> L2 fill reads from DRAM and ~3x longer epilogues), with 32-byte stores each sector is written once.
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6,
+                                             uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6),
+               "r"(a7)
+               : "memory");
+}
+// row segment of 32 values per lane -> global, in 32-byte pieces
+__device__ __forceinline__ void store_row32(float* p, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    st_global_v8(p + 8 * i, __float_as_uint(v[8 * i]), __float_as_uint(v[8 * i + 1]), __float_as_uint(v[8 * i + 2]), __float_as_uint(v[8 * i + 3]),
+                 __float_as_uint(v[8 * i + 4]), __float_as_uint(v[8 * i + 5]), __float_as_uint(v[8 * i + 6]), __float_as_uint(v[8 * i + 7]));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void store_row32(__nv_bfloat16* p, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+    st_global_v8(p + 16 * i, pack_bf16x2(v[16 * i], v[16 * i + 1]), pack_bf16x2(v[16 * i + 2], v[16 * i + 3]), pack_bf16x2(v[16 * i + 4], v[16 * i + 5]),
+                 pack_bf16x2(v[16 * i + 6], v[16 * i + 7]), pack_bf16x2(v[16 * i + 8], v[16 * i + 9]), pack_bf16x2(v[16 * i + 10], v[16 * i + 11]),
+                 pack_bf16x2(v[16 * i + 12], v[16 * i + 13]), pack_bf16x2(v[16 * i + 14], v[16 * i + 15]));
+}
 
 template <typename T, int NC> struct VecIO;
 template <int NC> struct VecIO<float, NC> {
@@ -101,13 +130,18 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int m, int n0, flo
     VecIO<float, NC>::load(xp, x);
 #pragma unroll
     for (int i = 0; i < NC; ++i) x[i] = fmaf(g[i], v[i], x[i]);     // x = x + gate * branch  (FMT.py:174-175)
-    VecIO<float, NC>::store(xp, x);
+    if constexpr (NC == 32) store_row32(xp, x);
+    else VecIO<float, NC>::store(xp, x);
     return;
   }
   if (p.out_f32) {
-    VecIO<float, NC>::store(reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.ldo + n0, v);
+    float* op = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.ldo + n0;
+    if constexpr (NC == 32) store_row32(op, v);
+    else VecIO<float, NC>::store(op, v);
   } else {
-    VecIO<AT, NC>::store(reinterpret_cast<AT*>(p.out) + static_cast<size_t>(m) * p.ldo + n0, v);
+    AT* op = reinterpret_cast<AT*>(p.out) + static_cast<size_t>(m) * p.ldo + n0;
+    if constexpr (NC == 32 && sizeof(AT) == 2) store_row32(reinterpret_cast<__nv_bfloat16*>(op), v);
+    else VecIO<AT, NC>::store(op, v);
   }
 }
 
@@ -239,6 +273,230 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair tcgen05 GEMM (cta_group::2): one 256 x BN output tile per pair of SMs.  Each CTA stages its own 128 rows of A
+// and HALF of the B tile (BN/2 weight rows); the leader CTA issues M = 256 UMMAs that read both halves, so the shared-memory
+// traffic per SM and per MMA drops from 12 KB to 8 KB (the single-CTA 128 x 256 tile is shared-memory-bandwidth bound:
+// 96 B/clk of operand reads + 96 B/clk of TMA fills against 128 B/clk).  Accumulators: 128 lanes x BN columns in EACH
+// CTA's TMEM, double buffered; each CTA's epilogue warps drain their own half.
+// Barriers: full (leader only, tx bytes of BOTH CTAs), empty / tmem-full (commit multicast to both CTAs),
+// tmem-empty (leader, 8 arrivals = 4 epilogue warps x 2 CTAs).
+// ------------------------------------------------------------------------------------------------
+// Tile rasterisation: tiles are walked in groups of GM row-tiles x all column-tiles (row fastest inside a group), so the
+// ~74 tiles in flight at any time cover a GM x (74/GM) block: every A tile is shared by ~74/GM tiles and every B tile by GM
+// tiles, instead of one B tile being requested by all SMs at once.
+__device__ __forceinline__ void raster_tile(int t, int m_tiles, int n_tiles, int gm, int& mt, int& nt) {
+  const int per_group = gm * n_tiles;
+  const int g = t / per_group, r = t - g * per_group;
+  const int m_in_group = min(gm, m_tiles - g * gm);
+  mt = g * gm + r % m_in_group;
+  nt = r / m_in_group;
+}
+
+template <int BN> struct Tc2Cfg {
+  static constexpr int BM = 256, BMH = 128, BK = 64, UMMA_K = 16;
+  static constexpr int A_BYTES = BMH * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int TMEM_COLS = ACC_STAGES * BN;
+  static constexpr int BAR_BYTES = 256 + BN * 4;        // barriers + tmem slot, then the tile's bias (BN floats)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int THREADS = 192;
+  static_assert(BN == 128 || BN == 256, "BN");
+};
+
+template <int BN, typename TT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Cfg<BN>::THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams ep, const int K) {
+  using C = Tc2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tfull_bar = empty_bar + C::STAGES;
+  uint64_t* tempty_bar = tfull_bar + C::ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + C::ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int num_kb = (K + C::BK - 1) / C::BK;
+  const int m_tiles = (ep.M + C::BM - 1) / C::BM;
+  const int n_tiles = (ep.N + BN - 1) / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < C::ACC_STAGES; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_cg2(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // the peer's barriers exist before anything is signalled across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs; bytes are counted on the leader's full barrier) =====================
+    if (lane == 0) {
+      pdl_wait_prior_grid();
+      int stage = 0; uint32_t phase = 0;
+      for (int t = pair; t < total_tiles; t += n_pairs) {
+        int mt, nt;
+        raster_tile(t, m_tiles, n_tiles, ep.raster_gm, mt, nt);
+        const int m0 = mt * C::BM + static_cast<int>(rank) * C::BMH;
+        const int n0 = nt * BN + static_cast<int>(rank) * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          tma_load_2d_cg2(&tmA, leader_full, sa, kb * C::BK, m0, kEvictNormal);
+          tma_load_2d_cg2(&tmB, leader_full, sa + C::A_BYTES, kb * C::BK, n0, kEvictNormal);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(C::BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = pair; t < total_tiles; t += n_pairs) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);        // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);              // both CTAs' TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint64_t da = make_sw128_kmajor_desc(sa);
+          const uint64_t db = make_sw128_kmajor_desc(sa + C::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < C::BK / C::UMMA_K; ++k) umma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_cg2(&empty_bar[stage], 0b11);        // frees the slot in BOTH CTAs when these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_cg2(&tfull_bar[acc], 0b11);            // accumulator complete -> both epilogues
+        if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps: this CTA's 128 rows =====================
+    // The epilogue of tile i runs under the MMAs of tile i+1, so it must stay shorter than one main loop (4.5 us at
+    // K = 1024).  Everything it reads from global memory is therefore requested ahead of use: the tile's bias goes to smem
+    // once, and the residual / gate / pos_embed operands of chunk c+1 are in flight while chunk c is computed (a first
+    // version that loaded them inside the chunk loop took 12 us per tile and made the whole GEMM epilogue-bound).
+    const int quarter = warp & 3;
+    const int et = threadIdx.x - 64;                        // 0..127 among the epilogue threads
+    float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);   // BN floats behind the barriers
+    pdl_wait_prior_grid();
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = pair; t < total_tiles; t += n_pairs) {
+      int mt, nt;
+      raster_tile(t, m_tiles, n_tiles, ep.raster_gm, mt, nt);
+      const int m0 = mt * C::BM + static_cast<int>(rank) * C::BMH, n0 = nt * BN;
+      const int m = m0 + quarter * 32 + lane;
+      const bool row_ok = m < ep.M;
+      const int mc = row_ok ? m : ep.M - 1;                 // clamped row: loads stay in bounds, stores are predicated
+      named_bar_sync(1, 128);                               // previous tile's readers of bias_s are done
+      for (int i = et; i < BN; i += 128) bias_s[i] = (ep.bias != nullptr && n0 + i < ep.N) ? ep.bias[n0 + i] : 0.f;
+      named_bar_sync(1, 128);
+      constexpr int NCH = BN / 32;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      if (ep.kind == EPI_GATE_RES) {
+        float* xrow = reinterpret_cast<float*>(ep.out) + static_cast<size_t>(mc) * ep.ldo + n0;
+        const TT* grow = reinterpret_cast<const TT*>(ep.gate) + static_cast<size_t>(ep.urow ? ep.urow[mc] : mc) * ep.ldg + ep.gate_off + n0;
+        float4 xq[2][8];
+        float gq[2][32];
+        auto prefetch = [&](int c, int b) {
+          if (n0 + c * 32 < ep.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xq[b][i] = *reinterpret_cast<const float4*>(xrow + c * 32 + i * 4);
+            VecIO<TT, 32>::load(grow + c * 32, gq[b]);
+          }
+        };
+        prefetch(0, 0);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          if (c + 1 < NCH) prefetch(c + 1, (c + 1) & 1);
+          float v[32];
+          tmem_ld32(t_addr + c * 32, v);
+          tmem_ld_wait();
+          if (row_ok && n0 + c * 32 < ep.N) {
+            float o[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {                                   // x = x + gate * branch  (FMT.py:174-175)
+              const float4 x = xq[c & 1][i];
+              o[4 * i] = fmaf(gq[c & 1][4 * i], v[4 * i] + bias_s[c * 32 + 4 * i], x.x);
+              o[4 * i + 1] = fmaf(gq[c & 1][4 * i + 1], v[4 * i + 1] + bias_s[c * 32 + 4 * i + 1], x.y);
+              o[4 * i + 2] = fmaf(gq[c & 1][4 * i + 2], v[4 * i + 2] + bias_s[c * 32 + 4 * i + 2], x.z);
+              o[4 * i + 3] = fmaf(gq[c & 1][4 * i + 3], v[4 * i + 3] + bias_s[c * 32 + 4 * i + 3], x.w);
+            }
+            store_row32(xrow + c * 32, o);
+          }
+        }
+      } else {
+        const float* prow = ep.kind == EPI_POS ? ep.pos + static_cast<size_t>(mc % ep.frames) * ep.N + n0 : nullptr;
+        float4 pq[2][8];
+        auto prefetch = [&](int c, int b) {
+          if (prow != nullptr && n0 + c * 32 < ep.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pq[b][i] = *reinterpret_cast<const float4*>(prow + c * 32 + i * 4);
+          }
+        };
+        prefetch(0, 0);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          if (c + 1 < NCH) prefetch(c + 1, (c + 1) & 1);
+          float v[32];
+          tmem_ld32(t_addr + c * 32, v);
+          tmem_ld_wait();
+          if (row_ok && n0 + c * 32 < ep.N) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += bias_s[c * 32 + i];
+            if (ep.kind == EPI_GELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+            } else if (ep.kind == EPI_POS) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { v[4 * i] += pq[c & 1][i].x; v[4 * i + 1] += pq[c & 1][i].y; v[4 * i + 2] += pq[c & 1][i].z; v[4 * i + 3] += pq[c & 1][i].w; }
+            }
+            if (ep.out_f32) store_row32(reinterpret_cast<float*>(ep.out) + static_cast<size_t>(m) * ep.ldo + n0 + c * 32, v);
+            else store_row32(reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(m) * ep.ldo + n0 + c * 32, v);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+      if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // nobody leaves while the peer may still read this CTA's smem or signal its barriers
+  if (warp == 2) tmem_dealloc_cg2(tmem_base, C::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -169,6 +169,9 @@ FMT_API int64_t fmt_debug_window_trace(const FmtHandle* h, int64_t* out, int64_t
 /* out[M,N] (fp32) = A[M,K] (bf16 bits) @ W[N,K]^T (bf16 bits) + bias[N], through the tcgen05/TMA GEMM. */
 FMT_API int32_t fmt_debug_gemm_bf16(const void* A, const void* W, const float* bias, float* out, int32_t M, int32_t N,
                                     int32_t K, int32_t block_n, void* stream);
+/* `iters` back-to-back launches of one GEMM variant (bf16 output); block_n as above, 512 / 1024 = CTA-pair kernel. */
+FMT_API int32_t fmt_debug_gemm_bench(const void* A, const void* W, const float* bias, float* out, int32_t M, int32_t N,
+                                     int32_t K, int32_t block_n, int32_t iters, void* stream);
 /* Same through the fp32 SIMT GEMM used by FMT_MODE_FP32_VALIDATE (A, W fp32). */
 FMT_API int32_t fmt_debug_gemm_fp32(const float* A, const float* W, const float* bias, float* out, int32_t M, int32_t N,
                                     int32_t K, void* stream);

@@ -38,6 +38,25 @@ def test_tcgen05_gemm_matches_torch(lib, M, N, K, block_n):
     assert err <= 2e-3 * max(1.0, ref.abs().max().item()), err   # fp32 accumulation error only
 
 
+@pytest.mark.parametrize("block_n", [512, 1024])     # CTA-pair kernel: 256 x 256 and 256 x 128 pair tiles
+@pytest.mark.parametrize("M,N,K", [(5760, 1024, 1024), (512, 256, 64), (300, 512, 128), (1620, 3072, 1024), (5760, 1024, 4096),
+                                    (51840, 512, 1088), (46080, 4096, 1024), (129, 256, 192)])
+def test_cta_pair_gemm_matches_torch(lib, M, N, K, block_n):
+    """cta_group::2 GEMM (two SMs per 256-row tile, B operand split across the pair)."""
+    L, cabi = lib
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    cabi.check(L.fmt_debug_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, block_n, _stream()), "gemm")
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + bias       # fp32 reference of the same bf16 operands (TF32 off by default for matmul)
+    err = (out - ref).abs().max().item()
+    assert torch.isfinite(out).all()
+    assert err <= 4e-3 * max(1.0, ref.abs().max().item()), err
+
+
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8])
 @pytest.mark.parametrize("M,N,K", [(180, 3072, 1024), (180, 1024, 4096), (60, 1024, 512), (240, 512, 1024), (180, 1024, 1088), (256, 4096, 1024), (17, 128, 64)])
 def test_skinny_gemm_matches_torch(lib, M, N, K, cluster, monkeypatch):

@@ -215,3 +215,28 @@ def test_window_kernel_matches_per_op_path(pkg, monkeypatch, method, nfe, nb_sca
         be.close()
     assert torch.isfinite(outs["1"]).all()
     assert cases.max_abs(outs["1"], outs["0"]) <= 1e-2, cases.max_abs(outs["1"], outs["0"])
+
+
+def test_large_batch_matches_oracle(pkg):
+    """32 clips per GPU (the tensor-pipe regime of BASELINE.json configs[3]): CTA-pair tcgen05 GEMMs + shared-memory band
+    attention, checked against the oracle run on the same device with the same injected noise."""
+    d = cases.FmtDims()
+    model = model_for(pkg, "full")
+    from oracle.synth import synth_inputs
+    B, T, nfe = 32, 70, 4
+    r_s, wa, we = synth_inputs(d, B, T, seed=123)
+    g = torch.Generator().manual_seed(9)
+    noise = torch.stack([torch.randn(B, d.frames_per_clip, d.dim_w, generator=g) for _ in range(2)])
+    out, _ = pkg.FloatSampleMotionSequenceRD_VA().sample_rd_sequence_va(r_s, wa, we, T, model, 2.0, 1.0, 1.0, False, nfe, "euler", 1e-5, 1e-5,
+                                                                       0.1, 0.1, 0.1, True, 9, _noise=noise)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    Wd = {k: v.to(DEV) for k, v in cases.weights("full").items()}
+    with torch.no_grad():
+        ref = O.sample_loop(Wd, d, r_s.to(DEV), wa.to(DEV), we.to(DEV), T, nfe=nfe, a_cfg_scale=2.0, r_cfg_scale=1.0, e_cfg_scale=1.0,
+                            noise=noise.to(DEV)).cpu()
+    assert out.shape == ref.shape == (B, T, d.dim_w)
+    assert cases.max_abs(out, ref) <= 2e-2, cases.max_abs(out, ref)
+    # clips never mix: clip 5 of the batch == the same clip sampled alone (different kernels -> bf16-level agreement)
+    solo, _ = pkg.FloatSampleMotionSequenceRD_VA().sample_rd_sequence_va(r_s[5:6], wa[5:6], we[5:6], T, model, 2.0, 1.0, 1.0, False, nfe, "euler",
+                                                                        1e-5, 1e-5, 0.1, 0.1, 0.1, True, 9, _noise=noise[:, 5:6].contiguous())
+    assert cases.max_abs(solo, out[5:6]) <= 1e-2, cases.max_abs(solo, out[5:6])
