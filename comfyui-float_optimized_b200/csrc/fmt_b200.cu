@@ -85,6 +85,7 @@ struct FmtHandle {
   DevBuf cond, cemb, temb, tfreq, th, silu, table, xstate, ystage, kbuf, prevx, ax, X, A1, QKV, A2, Hm, V, ddt, dteval, wargs;
   DevBuf st_rs, st_wa, st_we, st_noise, st_rd;   // staging for host-located clips
   DevBuf sk_scratch, sk_counters;                // split-K fix-up state of the skinny GEMM (kept all-zero between launches)
+  bool use_splitk = false;                       // 2-way K slicing of gate+residual GEMMs with a ragged last wave (FMT_SPLITK=1; measured 3 % slower at 32 clips)
   int raster_gm = 8;                             // FMT_RASTER_GM
   bool use_pair = true;                          // CTA-pair (cta_group::2) GEMM for M >= 512 (FMT_PAIR=0 disables)
   bool use_pdl = true;                           // programmatic dependent launch between graph nodes (FMT_PDL=0 disables)
@@ -196,7 +197,7 @@ static int launch_tc(FmtHandle* h, const bf16* A, int lda, const bf16* W, int ld
 }
 
 template <int BN>
-static int launch_tc2(FmtHandle* h, const bf16* A, int lda, const bf16* W, int ldw, const EpiParams& ep, int K, cudaStream_t st) {
+static int launch_tc2(FmtHandle* h, const bf16* A, int lda, const bf16* W, int ldw, const EpiParams& ep, int K, cudaStream_t st, int ksplit = 1) {
   using C = Tc2Cfg<BN>;
   static bool attr_set[64] = {};
   if (!attr_set[h->device & 63]) {
@@ -206,11 +207,12 @@ static int launch_tc2(FmtHandle* h, const bf16* A, int lda, const bf16* W, int l
   CUtensorMap ta, tb;
   FMT_OK(make_tmap(h, &ta, A, ep.M, K, lda, C::BMH));
   FMT_OK(make_tmap(h, &tb, W, ep.N, K, ldw, BN / 2));
-  const int tiles = ((ep.M + C::BM - 1) / C::BM) * ((ep.N + BN - 1) / BN);
+  const int tiles = ((ep.M + C::BM - 1) / C::BM) * ((ep.N + BN - 1) / BN) * ((ksplit > 1 && ep.kind == EPI_GATE_RES) ? ksplit : 1);
   const int max_pairs = h->num_sms / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   EpiParams ep2 = ep;
   ep2.raster_gm = h->raster_gm;
+  ep2.ksplit = (ksplit > 1 && ep.kind == EPI_GATE_RES) ? ksplit : 1;
   // the kernel carries __cluster_dims__(2,1,1); launch() only adds the PDL attribute
   return launch(h, gemm_tc2_kernel<BN, bf16>, dim3(2 * pairs), dim3(C::THREADS), C::SMEM_BYTES, st, 1, ta, tb, ep2, K);
 }
@@ -276,6 +278,12 @@ static int gemm_bf16(FmtHandle* h, const bf16* A, int lda, const bf16* W, int ld
     const double c_pair = waves(mt256 * (ep.N / 256), pairs);
     const double c_256 = waves(mt128 * (ep.N / 256), sms) * (ep.M >= 16384 ? 1.2 : 1.02);
     const double c_128 = waves(mt128 * (ep.N / 128), sms) * 0.56;
+    if (ep.kind == EPI_GATE_RES && h->use_splitk && K >= 1024 && c_pair >= 2.0) {   // single-wave problems stay bitwise deterministic
+      // x += gate * (.) is additive, so a tile may be cut into 2 K slices whose partial sums meet in x (fp32 RED):
+      // N = 1024 at 32 clips = 92 pair tiles on 74 pairs (2 waves) -> 184 half-K units (2.5 half-waves)
+      const double c_split = 0.5 * waves(2 * mt256 * (ep.N / 256), pairs) + 0.08;
+      if (c_split < c_pair && c_split < c_256 && c_split < c_128) return launch_tc2<256>(h, A, lda, W, ldw, ep, K, st, 2);
+    }
     if (c_pair <= c_256 && c_pair <= c_128) return launch_tc2<256>(h, A, lda, W, ldw, ep, K, st);
     return c_128 < c_256 ? launch_tc<128>(h, A, lda, W, ldw, ep, K, st) : launch_tc<256>(h, A, lda, W, ldw, ep, K, st);
   }
@@ -365,16 +373,13 @@ static int launch_attn(FmtHandle* h, cudaStream_t st) {
   const int win = h->d.attention_window;
   if constexpr (sizeof(T) == 2) {
     // many sequences: one CTA per (sequence, head) with K / V staged in shared memory (every qkv byte read once)
-    const size_t tile_smem = static_cast<size_t>(2) * s.N * hd * sizeof(bf16);
-    if (n_seq * heads >= 2 * h->num_sms && tile_smem <= 48 * 1024 && hd % 8 == 0) {
+    const size_t tile_smem = static_cast<size_t>(3) * s.N * hd * sizeof(bf16);   // Q, K, V of one (sequence, head)
+    if (n_seq * heads >= 2 * h->num_sms && tile_smem <= 48 * 1024 && (hd == 64 || hd == 128)) {
       const bf16* q16 = reinterpret_cast<const bf16*>(qkv);
       bf16* o16 = reinterpret_cast<bf16*>(out);
       const dim3 tg(n_seq * heads), tb(128);
-      switch (hd) {
-        case 32: return launch(h, band_attention_tile_kernel<1>, tg, tb, tile_smem, st, 1, q16, s.N, heads, win, scale, o16);
-        case 64: return launch(h, band_attention_tile_kernel<2>, tg, tb, tile_smem, st, 1, q16, s.N, heads, win, scale, o16);
-        case 128: return launch(h, band_attention_tile_kernel<4>, tg, tb, tile_smem, st, 1, q16, s.N, heads, win, scale, o16);
-      }
+      if (hd == 64) return launch(h, band_attention_tile_kernel<64>, tg, tb, tile_smem, st, 1, q16, s.N, heads, win, scale, o16);
+      return launch(h, band_attention_tile_kernel<128>, tg, tb, tile_smem, st, 1, q16, s.N, heads, win, scale, o16);
     }
   }
   switch (hd) {
@@ -686,6 +691,7 @@ int32_t fmt_create(const FmtDims* dims, const void* const* wp, int32_t n_ptrs, i
   if (const char* e = getenv("FMT_SKINNY")) h->use_skinny = atoi(e) != 0;
   if (const char* e = getenv("FMT_WINDOW")) h->use_window = atoi(e) != 0;
   if (const char* e = getenv("FMT_PAIR")) h->use_pair = atoi(e) != 0;
+  if (const char* e = getenv("FMT_SPLITK")) h->use_splitk = atoi(e) != 0;
   if (const char* e = getenv("FMT_RASTER_GM")) { int v = atoi(e); if (v >= 1) h->raster_gm = v; }
   if (const char* e = getenv("FMT_WIN_PK")) sscanf(e, "%d,%d,%d,%d", &h->win_pk[0], &h->win_pk[1], &h->win_pk[2], &h->win_pk[3]);
   if (const char* e = getenv("FMT_SK_CLUSTER")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) h->sk_cluster = v; }

@@ -27,6 +27,7 @@ struct EpiParams {
   long long ldg;
   long long gate_off;
   int raster_gm;       // CTA-pair kernel: row-tiles per raster group (>= 1)
+  int ksplit;          // CTA-pair kernel, EPI_GATE_RES only: K slices per tile (0/1 = none); partial sums meet in x through fp32 RED
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -34,6 +35,14 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   float u = k0 * (x + k1 * x * x * x);
   return 0.5f * x * (1.0f + tanhf(u));
+}
+
+__device__ __forceinline__ float gelu_tanh_approx(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u = k0 * (x + k1 * x * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * (1.0f + t);
 }
 
 template <typename T> __device__ __forceinline__ float to_f32(T v);
@@ -48,6 +57,9 @@ __device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, 
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6),
                "r"(a7)
                : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 // row segment of 32 values per lane -> global, in 32-byte pieces
 __device__ __forceinline__ void store_row32(float* p, const float (&v)[32]) {
@@ -116,7 +128,7 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int m, int n0, flo
   }
   if (p.kind == EPI_GELU) {
 #pragma unroll
-    for (int i = 0; i < NC; ++i) v[i] = gelu_tanh(v[i]);
+    for (int i = 0; i < NC; ++i) v[i] = sizeof(AT) == 2 ? gelu_tanh_approx(v[i]) : gelu_tanh(v[i]);   // bf16 output: tanh.approx (2^-11) is below its rounding
   } else if (p.kind == EPI_POS) {
     float b[NC];
     VecIO<float, NC>::load(p.pos + static_cast<size_t>(m % p.frames) * p.N + n0, b);
@@ -326,7 +338,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int num_kb = (K + C::BK - 1) / C::BK;
   const int m_tiles = (ep.M + C::BM - 1) / C::BM;
   const int n_tiles = (ep.N + BN - 1) / BN;
-  const int total_tiles = m_tiles * n_tiles;
+  const int ksplit = ep.ksplit > 1 ? ep.ksplit : 1;
+  const int total_units = m_tiles * n_tiles * ksplit;           // unit = (tile, K slice); slices of a tile are consecutive units
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
@@ -354,12 +367,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       pdl_wait_prior_grid();
       int stage = 0; uint32_t phase = 0;
-      for (int t = pair; t < total_tiles; t += n_pairs) {
+      for (int u = pair; u < total_units; u += n_pairs) {
         int mt, nt;
-        raster_tile(t, m_tiles, n_tiles, ep.raster_gm, mt, nt);
+        raster_tile(u / ksplit, m_tiles, n_tiles, ep.raster_gm, mt, nt);
+        const int ks = u % ksplit, kb_lo = ks * num_kb / ksplit, kb_hi = (ks + 1) * num_kb / ksplit;
         const int m0 = mt * C::BM + static_cast<int>(rank) * C::BMH;
         const int n0 = nt * BN + static_cast<int>(rank) * (BN / 2);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
@@ -377,18 +391,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       constexpr uint32_t idesc = make_idesc_bf16_f32(C::BM, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = pair; t < total_tiles; t += n_pairs) {
+      for (int u = pair; u < total_units; u += n_pairs) {
+        const int ks = u % ksplit, kb_lo = ks * num_kb / ksplit, kb_hi = (ks + 1) * num_kb / ksplit;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);        // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&full_bar[stage], phase);              // both CTAs' TMA bytes have landed
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t da = make_sw128_kmajor_desc(sa);
           const uint64_t db = make_sw128_kmajor_desc(sa + C::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < C::BK / C::UMMA_K; ++k) umma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < C::BK / C::UMMA_K; ++k) umma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
           umma_commit_cg2(&empty_bar[stage], 0b11);        // frees the slot in BOTH CTAs when these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -408,15 +423,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);   // BN floats behind the barriers
     pdl_wait_prior_grid();
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = pair; t < total_tiles; t += n_pairs) {
+    for (int u = pair; u < total_units; u += n_pairs) {
       int mt, nt;
-      raster_tile(t, m_tiles, n_tiles, ep.raster_gm, mt, nt);
+      raster_tile(u / ksplit, m_tiles, n_tiles, ep.raster_gm, mt, nt);
+      const bool first_slice = (u % ksplit) == 0;            // the bias joins the sum exactly once
       const int m0 = mt * C::BM + static_cast<int>(rank) * C::BMH, n0 = nt * BN;
       const int m = m0 + quarter * 32 + lane;
       const bool row_ok = m < ep.M;
       const int mc = row_ok ? m : ep.M - 1;                 // clamped row: loads stay in bounds, stores are predicated
       named_bar_sync(1, 128);                               // previous tile's readers of bias_s are done
-      for (int i = et; i < BN; i += 128) bias_s[i] = (ep.bias != nullptr && n0 + i < ep.N) ? ep.bias[n0 + i] : 0.f;
+      for (int i = et; i < BN; i += 128) bias_s[i] = (ep.bias != nullptr && first_slice && n0 + i < ep.N) ? ep.bias[n0 + i] : 0.f;
       named_bar_sync(1, 128);
       constexpr int NCH = BN / 32;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
@@ -427,8 +443,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         float gq[2][32];
         auto prefetch = [&](int c, int b) {
           if (n0 + c * 32 < ep.N) {
+            if (ksplit == 1) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) xq[b][i] = *reinterpret_cast<const float4*>(xrow + c * 32 + i * 4);
+              for (int i = 0; i < 8; ++i) xq[b][i] = *reinterpret_cast<const float4*>(xrow + c * 32 + i * 4);
+            }
             VecIO<TT, 32>::load(grow + c * 32, gq[b]);
           }
         };
@@ -441,7 +459,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           float v[32];
           tmem_ld32(t_addr + c * 32, v);
           tmem_ld_wait();
-          if (row_ok && n0 + c * 32 < ep.N) {
+          if (row_ok && n0 + c * 32 < ep.N && ksplit > 1) {
+            // K-sliced tile: x += gate * partial, summed in L2 by fp32 RED (the order of the slices is not fixed)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              red_add_v4(xrow + c * 32 + i * 4, gq[c & 1][4 * i] * (v[4 * i] + bias_s[c * 32 + 4 * i]), gq[c & 1][4 * i + 1] * (v[4 * i + 1] + bias_s[c * 32 + 4 * i + 1]),
+                         gq[c & 1][4 * i + 2] * (v[4 * i + 2] + bias_s[c * 32 + 4 * i + 2]), gq[c & 1][4 * i + 3] * (v[4 * i + 3] + bias_s[c * 32 + 4 * i + 3]));
+          } else if (row_ok && n0 + c * 32 < ep.N) {
             float o[32];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {                                   // x = x + gate * branch  (FMT.py:174-175)
@@ -477,7 +501,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int i = 0; i < 32; ++i) v[i] += bias_s[c * 32 + i];
             if (ep.kind == EPI_GELU) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+              for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_approx(v[i]);   // tanh.approx: 2^-11, below the bf16 rounding of the output
             } else if (ep.kind == EPI_POS) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) { v[4 * i] += pq[c & 1][i].x; v[4 * i + 1] += pq[c & 1][i].y; v[4 * i + 2] += pq[c & 1][i].z; v[4 * i + 3] += pq[c & 1][i].w; }
