@@ -40,6 +40,14 @@ def peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def measured_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r01_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(key, {})
+    return {}
+
+
 def algorithmic_work(dims, B, nb, S):
     """Per-window algorithmic bytes / FLOPs, bf16 weights, AdaLN tables hoisted."""
     H, W, M, D, N = dims.dim_h, dims.dim_w, dims.mlp_hidden, dims.fmt_depth, dims.total_frames
@@ -276,11 +284,15 @@ def main():
     hbm_achieved = work["window_bytes"] / t_window / 1e9
     tf_achieved = work["window_flops"] / t_window / 1e12
     hbm_frac, tf_frac = hbm_achieved / pk["hbm_gbs"], tf_achieved / pk["bf16_tflops_sustained"]
-    if hbm_frac >= tf_frac:
-        roof = dict(bound="hbm", achieved=hbm_achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=hbm_frac, traffic=None)
+    # Which roofline binds is a property of the workload: <= 2 clips stream the weights (180 flop/B per clip
+    # against a ridge of ~210), >= 8 clips are dense-contraction bound.
+    prof = measured_traffic("b1_window" if work["rows"] <= 256 else "b32")
+    if work["rows"] <= 512:
+        roof = dict(bound="hbm", achieved=hbm_achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=hbm_frac, traffic=prof.get("dram_bytes_per_launch"))
     else:
-        roof = dict(bound="tensor", achieved=tf_achieved, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s", frac=tf_frac, traffic=None)
-    roof.update(peak_source=pk["source"], launch="one captured window graph = prepare + %d ODE steps" % S,
+        roof = dict(bound="tensor", achieved=tf_achieved, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s", frac=tf_frac, traffic=prof.get("dram_bytes_per_launch"))
+    roof.update(peak_source=pk["source"], launch="one captured window graph = prepare + %d ODE steps" % S, dominant_kernel=prof.get("kernel"),
+                traffic_source=prof.get("source"),
                 us_per_ode_step=1e6 * t_window / S, algorithmic_bytes_per_window=work["window_bytes"],
                 algorithmic_flops_per_window=work["window_flops"], other_bound_frac=min(hbm_frac, tf_frac))
     h2d = (r_s.numel() + wa.numel() + we.numel()) * 4
