@@ -240,3 +240,50 @@ def test_large_batch_matches_oracle(pkg):
     solo, _ = pkg.FloatSampleMotionSequenceRD_VA().sample_rd_sequence_va(r_s[5:6], wa[5:6], we[5:6], T, model, 2.0, 1.0, 1.0, False, nfe, "euler",
                                                                         1e-5, 1e-5, 0.1, 0.1, 0.1, True, 9, _noise=noise[:, 5:6].contiguous())
     assert cases.max_abs(solo, out[5:6]) <= 1e-2, cases.max_abs(solo, out[5:6])
+
+
+def _oracle_on_gpu(d, r_s, wa, we, T, noise, **kw):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    Wd = {k: v.to(DEV) for k, v in cases.weights("full").items()}
+    with torch.no_grad():
+        return O.sample_loop(Wd, d, r_s.to(DEV), wa.to(DEV), we.to(DEV), T, noise=noise.to(DEV), **kw).cpu()
+
+
+def test_long_clip_chained_windows(pkg):
+    """BASELINE.json configs[2] in miniature: one clip, 12 sequential windows chained through prev_x / prev_wa (bf16 error
+    accumulates across windows, SURVEY.md §7 'hard parts'), free-running against the oracle on the same noise."""
+    d = cases.FmtDims()
+    model = model_for(pkg, "full")
+    from oracle.synth import synth_inputs
+    T, nfe = 590, 10                                              # 12 windows, ragged last one
+    r_s, wa, we = synth_inputs(d, 1, T, seed=31)
+    g = torch.Generator().manual_seed(4)
+    noise = torch.stack([torch.randn(1, d.frames_per_clip, d.dim_w, generator=g) for _ in range(12)])
+    node = pkg.FloatSampleMotionSequenceRD_VA()
+    args = (2.0, 1.0, 1.0, False, nfe, "euler", 1e-5, 1e-5, 0.1, 0.1, 0.1, True, 4)
+    out, _ = node.sample_rd_sequence_va(r_s, wa, we, T, model, *args, _noise=noise)
+    ref = _oracle_on_gpu(d, r_s, wa, we, T, noise, nfe=nfe, a_cfg_scale=2.0, r_cfg_scale=1.0, e_cfg_scale=1.0)
+    assert out.shape == ref.shape == (1, T, d.dim_w)
+    assert cases.max_abs(out, ref) <= 2e-2, cases.max_abs(out, ref)
+    per_window = [(cases.max_abs(out[:, s:s + 50], ref[:, s:s + 50])) for s in range(0, T, 50)]
+    assert max(per_window[6:]) <= 4 * max(max(per_window[:6]), 1e-3), per_window      # no blow-up along the chain
+    out32, _ = node.sample_rd_sequence_va(r_s, wa, we, T, model, *args, _mode="fp32", _noise=noise)
+    assert cases.rel_err(out32, ref) <= 1e-4, cases.rel_err(out32, ref)
+
+
+@pytest.mark.parametrize("nfe,a,e", [(5, 1.0, 3.0), (20, 3.0, 1.0), (10, 4.0, 3.0), (10, 1.0, 1.0)])
+def test_dynamic_emotion_sweeps(pkg, nfe, a, e):
+    """BASELINE.json configs[4]: per-window (dynamic) emotion vectors, nfe sweep 5/10/20, a_cfg sweep 1-4 (a = e = 1 takes the
+    single-branch path, FMT.py:400-401); 2 clips, 2.5 windows."""
+    d = cases.FmtDims()
+    model = model_for(pkg, "full")
+    from oracle.synth import synth_inputs
+    B, T = 2, 125
+    r_s, wa, we = synth_inputs(d, B, T, seed=77, dynamic_we=True)
+    assert we.shape == (B, T, d.dim_e)
+    g = torch.Generator().manual_seed(8)
+    noise = torch.stack([torch.randn(B, d.frames_per_clip, d.dim_w, generator=g) for _ in range(3)])
+    out, _ = pkg.FloatSampleMotionSequenceRD_VA().sample_rd_sequence_va(r_s, wa, we, T, model, a, 1.0, e, False, nfe, "euler", 1e-5, 1e-5,
+                                                                       0.1, 0.1, 0.1, True, 8, _noise=noise)
+    ref = _oracle_on_gpu(d, r_s, wa, we, T, noise, nfe=nfe, a_cfg_scale=a, r_cfg_scale=1.0, e_cfg_scale=e)
+    assert cases.max_abs(out, ref) <= 2e-2, cases.max_abs(out, ref)
