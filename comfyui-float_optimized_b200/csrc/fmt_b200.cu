@@ -5,7 +5,6 @@
 // which runs entirely on the device: windows are chained through prev_x / prev_wa / prev_we without host syncs.
 #include "../../include/fmt_b200.h"
 #include "kernels.cuh"
-#include "skinny.cuh"
 #include "window.cuh"
 
 #include <cstdlib>
@@ -84,21 +83,17 @@ struct FmtHandle {
   // workspace
   DevBuf cond, cemb, temb, tfreq, th, silu, table, xstate, ystage, kbuf, prevx, ax, X, A1, QKV, A2, Hm, V, ddt, dteval, wargs;
   DevBuf st_rs, st_wa, st_we, st_noise, st_rd;   // staging for host-located clips
-  DevBuf sk_scratch, sk_counters;                // split-K fix-up state of the skinny GEMM (kept all-zero between launches)
   bool use_splitk = false;                       // 2-way K slicing of gate+residual GEMMs with a ragged last wave (FMT_SPLITK=1; measured 3 % slower at 32 clips)
   int raster_gm = 8;                             // FMT_RASTER_GM
   bool use_pair = true;                          // CTA-pair (cta_group::2) GEMM for M >= 512 (FMT_PAIR=0 disables)
   bool use_pdl = true;                           // programmatic dependent launch between graph nodes (FMT_PDL=0 disables)
-  bool use_skinny = false;                       // atomic split-K skinny-M GEMM (FMT_SKINNY=1 enables; measured slower than the tiled path, kept for tests)
-  int sk_cluster = 8;                            // cluster size of the skinny GEMM (FMT_SK_CLUSTER)
-  int sk_target_ctas = 128;                      // K-split until about this many CTAs (FMT_SK_CTAS)
   size_t ws_bytes = 0;
 
   // persistent window kernel (window.cuh): used when the plan has <= 256 token rows in bf16 mode
   bool use_window = true;                        // FMT_WINDOW=0 disables (falls back to one kernel per op)
   bool window_active = false;
   int win_pk[4] = {0, 0, 0, 0};                  // K-split overrides for qkv / proj / fc1 / fc2 (FMT_WIN_PK="q,p,1,2"; 0 = auto)
-  DevBuf win_params, win_tmaps, win_acc, win_bar, win_trace;
+  DevBuf win_params, win_tmaps, win_acc, win_bar, win_trace, win_act;   // win_act: pre-tiled A1 | A2 | Hm operands
   int win_trace_stride = 0;
   int* win_err_host = nullptr;                   // mapped pinned int: which bounded spin tripped (0 = none)
   int* win_err_dev = nullptr;
@@ -217,43 +212,6 @@ static int launch_tc2(FmtHandle* h, const bf16* A, int lda, const bf16* W, int l
   return launch(h, gemm_tc2_kernel<BN, bf16>, dim3(2 * pairs), dim3(C::THREADS), C::SMEM_BYTES, st, 1, ta, tb, ep2, K);
 }
 
-// ---- skinny-M path (weights as the UMMA M operand, all rows as N; see skinny.cuh)
-static int make_tmap_box(FmtHandle* h, CUtensorMap* m, const void* ptr, int rows, int cols, int ld_elems, int box_rows);
-
-static int gemm_skinny(FmtHandle* h, const bf16* A, int lda, const bf16* W, int ldw, const EpiParams& ep, int K, cudaStream_t st) {
-  static bool attr_set[64] = {};
-  int CL = h->sk_cluster;
-  const int n_ft = ep.N / 128;
-  while (CL > 1 && n_ft % CL != 0) CL >>= 1;
-  const int align = 8 * CL > 16 ? 8 * CL : 16;
-  int Mpad = ((ep.M + align - 1) / align) * align;
-  while (Mpad > 256 && CL > 1) { CL >>= 1; const int al = 8 * CL > 16 ? 8 * CL : 16; Mpad = ((ep.M + al - 1) / al) * al; }
-  REQUIRE(Mpad <= 256, "gemm_skinny: M=%d too large", ep.M);
-  const int nkb = K / 64;
-  // K-split: largest divisor of nkb that keeps the grid at or below the CTA target
-  int n_ks = 1;
-  for (int d = 1; d <= nkb; ++d)
-    if (nkb % d == 0 && n_ft * d <= h->sk_target_ctas) n_ks = d;
-  SkinnyParams sp{};
-  sp.ep = ep; sp.K = K; sp.Mpad = Mpad; sp.n_ft = n_ft; sp.n_ks = n_ks; sp.kb_per_split = nkb / n_ks;
-  sp.scratch = static_cast<float*>(h->sk_scratch.p); sp.counters = static_cast<int*>(h->sk_counters.p);
-  if (n_ks > 1 && ep.kind != EPI_GATE_RES)
-    REQUIRE(static_cast<size_t>(ep.M) * ep.N * 4 <= h->sk_scratch.bytes && static_cast<size_t>(n_ft) * 4 <= h->sk_counters.bytes,
-            "gemm_skinny: split-K scratch too small");
-  const int smem = sk_smem_bytes(Mpad);
-  if (!attr_set[h->device & 63]) {
-    CUDA_OK(cudaFuncSetAttribute(skinny_gemm_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem_bytes(256)));
-    attr_set[h->device & 63] = true;
-  }
-  CUtensorMap tw, ta;
-  FMT_OK(make_tmap_box(h, &tw, W, ep.N, K, ldw, 128));
-  FMT_OK(make_tmap_box(h, &ta, A, ep.M, K, lda, Mpad / CL));
-  return launch(h, skinny_gemm_kernel<bf16>, dim3(n_ft * n_ks), dim3(SK_THREADS), smem, st, CL, tw, ta, sp);
-}
-static int make_tmap_box(FmtHandle* h, CUtensorMap* m, const void* ptr, int rows, int cols, int ld_elems, int box_rows) {
-  return make_tmap(h, m, ptr, rows, cols, ld_elems, box_rows);
-}
-
 static int pick_bn(const FmtHandle* h, int M, int N) {
   const int mt = (M + 127) / 128;
   if (N % 256 == 0 && mt * (N / 256) >= 2 * h->num_sms) return 256;
@@ -263,8 +221,6 @@ static int pick_bn(const FmtHandle* h, int M, int N) {
 
 static int gemm_bf16(FmtHandle* h, const bf16* A, int lda, const bf16* W, int ldw, const EpiParams& ep, int K, cudaStream_t st, int force_bn = 0) {
   REQUIRE(ep.N % 32 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm_bf16: N %% 32, K/lda/ldw %% 8 required (N=%d K=%d)", ep.N, K);
-  if (force_bn == -1 || (force_bn == 0 && h->use_skinny && ep.M <= 256 && ep.N % 128 == 0 && K % 64 == 0 && h->sk_scratch.p != nullptr))
-    return gemm_skinny(h, A, lda, W, ldw, ep, K, st);
   // CTA-pair kernel (force_bn 512 / 1024 = pair tiles 256x256 / 256x128): the default once there are enough 256-row tiles
   if (force_bn == 512) return launch_tc2<256>(h, A, lda, W, ldw, ep, K, st);
   if (force_bn == 1024) return launch_tc2<128>(h, A, lda, W, ldw, ep, K, st);
@@ -472,7 +428,11 @@ static int setup_window(FmtHandle* h, cudaStream_t st) {
   float* arena = static_cast<float*>(h->win_acc.p);
   wp.Pacc = arena; wp.QKVacc = arena + n_p; wp.Hacc = wp.QKVacc + n_q; wp.Vacc = wp.Hacc + n_h;
   wp.X = static_cast<float*>(h->X.p);
-  wp.A1 = static_cast<bf16*>(h->A1.p); wp.A2 = static_cast<bf16*>(h->A2.p); wp.Hm = static_cast<bf16*>(h->Hm.p); wp.ax = static_cast<bf16*>(h->ax.p);
+  // pre-tiled operands: [K block][Rp][64] bf16 each, zero-filled once (rows >= R are never written)
+  const size_t t_a1 = static_cast<size_t>((H + 63) / 64) * Rp * 64, t_hm = static_cast<size_t>((M4 + 63) / 64) * Rp * 64;
+  FMT_OK(dev_alloc(h, h->win_act, (2 * t_a1 + t_hm) * sizeof(bf16)));
+  CUDA_OK(cudaMemsetAsync(h->win_act.p, 0, h->win_act.bytes, st));
+  wp.A1 = static_cast<bf16*>(h->win_act.p); wp.A2 = wp.A1 + t_a1; wp.Hm = wp.A2 + t_a1; wp.ax = static_cast<bf16*>(h->ax.p);
   wp.table = static_cast<const bf16*>(h->table.p);
   wp.b_x = h->x_emb.b; wp.pos = h->pos; wp.b_dec = h->dec.b;
   for (int i = 0; i < D; ++i) { wp.b_qkv[i] = h->qkv[i].b; wp.b_proj[i] = h->proj[i].b; wp.b_fc1[i] = h->fc1[i].b; wp.b_fc2[i] = h->fc2[i].b; }
@@ -497,9 +457,7 @@ static int setup_window(FmtHandle* h, cudaStream_t st) {
   const int C_P = n_gemms + 4, C_Q = n_gemms + 5, C_H = n_gemms + 6, C_V = n_gemms + 7;
   const CUtensorMapDataType BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   FMT_OK(make_tmap_ex(h, &maps[A_AX], wp.ax, BF, 2, R, W, W, 64, Rp, CU_TENSOR_MAP_SWIZZLE_128B));
-  FMT_OK(make_tmap_ex(h, &maps[A_A1], wp.A1, BF, 2, R, H, H, 64, Rp, CU_TENSOR_MAP_SWIZZLE_128B));
-  FMT_OK(make_tmap_ex(h, &maps[A_A2], wp.A2, BF, 2, R, H, H, 64, Rp, CU_TENSOR_MAP_SWIZZLE_128B));
-  FMT_OK(make_tmap_ex(h, &maps[A_HM], wp.Hm, BF, 2, R, M4, M4, 64, Rp, CU_TENSOR_MAP_SWIZZLE_128B));
+  maps[A_A1] = maps[A_AX]; maps[A_A2] = maps[A_AX]; maps[A_HM] = maps[A_AX];   // A1 / A2 / Hm are pre-tiled: fetched with bulk copies, no tensor map
   FMT_OK(make_tmap_ex(h, &maps[C_P], wp.Pacc, F32, 4, R, H, H, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
   FMT_OK(make_tmap_ex(h, &maps[C_Q], wp.QKVacc, F32, 4, R, 3 * H, 3 * H, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
   FMT_OK(make_tmap_ex(h, &maps[C_H], wp.Hacc, F32, 4, R, M4, M4, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
@@ -509,6 +467,8 @@ static int setup_window(FmtHandle* h, cudaStream_t st) {
   auto plan_gemm = [&](int g, const Linear& L, int tm_a, int tm_acc, int pk_override) -> int {
     WinGemm& G = wp.gemms[g];
     G.tm_w = g; G.tm_a = tm_a; G.tm_acc = tm_acc;
+    G.a_tiled = 0;
+    if (tm_a == A_A1 || tm_a == A_A2 || tm_a == A_HM) { G.a_tiled = 1; G.tm_a = tm_a == A_A1 ? 0 : tm_a == A_A2 ? 1 : 2; }
     G.n_ft = (L.N + 127) / 128;
     G.nkb = (L.K + 63) / 64;
     REQUIRE(G.n_ft <= grid, "window kernel: %d feature tiles > %d SMs", G.n_ft, grid);
@@ -688,14 +648,11 @@ int32_t fmt_create(const FmtDims* dims, const void* const* wp, int32_t n_ptrs, i
   h->Kc = ((d.dim_w + d.dim_a + d.dim_e + 63) / 64) * 64;
   h->NT = d.depth * 6 * d.dim_h + 2 * d.dim_h;
   if (const char* e = getenv("FMT_PDL")) h->use_pdl = atoi(e) != 0;
-  if (const char* e = getenv("FMT_SKINNY")) h->use_skinny = atoi(e) != 0;
   if (const char* e = getenv("FMT_WINDOW")) h->use_window = atoi(e) != 0;
   if (const char* e = getenv("FMT_PAIR")) h->use_pair = atoi(e) != 0;
   if (const char* e = getenv("FMT_SPLITK")) h->use_splitk = atoi(e) != 0;
   if (const char* e = getenv("FMT_RASTER_GM")) { int v = atoi(e); if (v >= 1) h->raster_gm = v; }
   if (const char* e = getenv("FMT_WIN_PK")) sscanf(e, "%d,%d,%d,%d", &h->win_pk[0], &h->win_pk[1], &h->win_pk[2], &h->win_pk[3]);
-  if (const char* e = getenv("FMT_SK_CLUSTER")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) h->sk_cluster = v; }
-  if (const char* e = getenv("FMT_SK_CTAS")) { int v = atoi(e); if (v >= 1) h->sk_target_ctas = v; }
   {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -769,8 +726,8 @@ int32_t fmt_destroy(FmtHandle* h) {
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   for (void* p : h->owned) cudaFree(p);
   DevBuf* bufs[] = {&h->cond, &h->cemb, &h->temb, &h->tfreq, &h->th, &h->silu, &h->table, &h->xstate, &h->ystage, &h->kbuf, &h->prevx, &h->ax,
-                    &h->X, &h->A1, &h->QKV, &h->A2, &h->Hm, &h->V, &h->ddt, &h->dteval, &h->wargs, &h->st_rs, &h->st_wa, &h->st_we, &h->st_noise, &h->st_rd, &h->sk_scratch, &h->sk_counters,
-                    &h->win_params, &h->win_tmaps, &h->win_acc, &h->win_bar, &h->win_trace};
+                    &h->X, &h->A1, &h->QKV, &h->A2, &h->Hm, &h->V, &h->ddt, &h->dteval, &h->wargs, &h->st_rs, &h->st_wa, &h->st_we, &h->st_noise, &h->st_rd,
+                    &h->win_params, &h->win_tmaps, &h->win_acc, &h->win_bar, &h->win_trace, &h->win_act};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->win_err_host) cudaFreeHost(h->win_err_host);
@@ -878,18 +835,6 @@ int32_t fmt_configure(FmtHandle* h, const FmtPlan* p, void* stream) {
   FMT_OK(dev_alloc(h, h->dteval, static_cast<size_t>(ne > 0 ? ne : 1) * 4));
   FMT_OK(dev_alloc(h, h->wargs, sizeof(WindowArgs)));
   CUDA_OK(cudaMemsetAsync(h->prevx.p, 0, h->prevx.bytes, st));
-  if (R <= 256 && p->mode == FMT_MODE_BF16) {
-    size_t maxN = h->NT > d.mlp_hidden ? h->NT : d.mlp_hidden;
-    if (maxN < 3 * H) maxN = 3 * H;
-    const bool fresh = h->sk_scratch.bytes < 256 * maxN * 4 || !h->sk_counters.p;
-    FMT_OK(dev_alloc(h, h->sk_scratch, 256 * maxN * 4));
-    FMT_OK(dev_alloc(h, h->sk_counters, 4096));
-    if (fresh) {
-      CUDA_OK(cudaMemsetAsync(h->sk_scratch.p, 0, h->sk_scratch.bytes, st));
-      CUDA_OK(cudaMemsetAsync(h->sk_counters.p, 0, h->sk_counters.bytes, st));
-    }
-  }
-
   if (ne > 0) {
     // timestep embeddings of every evaluation (FMT.py:294), computed once per plan
     CUDA_OK(cudaMemcpyAsync(h->dteval.p, h->t_eval.data(), ne * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -905,6 +850,22 @@ int32_t fmt_configure(FmtHandle* h, const FmtPlan* p, void* stream) {
   }
 
   h->window_active = window_eligible(h, p) && h->table_chunk == ne;
+  if (h->window_active) {
+    // the persistent kernel synchronises across the grid: it needs one resident CTA on every SM, else the plan runs one kernel per op
+    int occ = 0;
+    cudaError_t oe = cudaErrorUnknown;
+    switch (d.dim_h / 128) {
+      case 1: oe = cudaFuncSetAttribute(fmt_window_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM_BYTES);
+              if (oe == cudaSuccess) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fmt_window_kernel<1>, WIN_THREADS, WIN_SMEM_BYTES); break;
+      case 2: oe = cudaFuncSetAttribute(fmt_window_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM_BYTES);
+              if (oe == cudaSuccess) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fmt_window_kernel<2>, WIN_THREADS, WIN_SMEM_BYTES); break;
+      case 4: oe = cudaFuncSetAttribute(fmt_window_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM_BYTES);
+              if (oe == cudaSuccess) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fmt_window_kernel<4>, WIN_THREADS, WIN_SMEM_BYTES); break;
+      case 8: oe = cudaFuncSetAttribute(fmt_window_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM_BYTES);
+              if (oe == cudaSuccess) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fmt_window_kernel<8>, WIN_THREADS, WIN_SMEM_BYTES); break;
+    }
+    if (oe != cudaSuccess || occ < 1) { (void)cudaGetLastError(); h->window_active = false; }
+  }
   if (h->window_active) FMT_OK(setup_window(h, st));
 
   // capture one window as a CUDA graph
@@ -1041,22 +1002,8 @@ int32_t fmt_debug_gemm_bf16(const void* A, const void* W, const float* bias, flo
   FMT_OK(debug_handle(h));
   h.use_pdl = false;
   if (const char* e = getenv("FMT_RASTER_GM")) { int v = atoi(e); if (v >= 1) h.raster_gm = v; }
-  if (const char* e = getenv("FMT_SK_CLUSTER")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) h.sk_cluster = v; }
-  if (const char* e = getenv("FMT_SK_CTAS")) { int v = atoi(e); if (v >= 1) h.sk_target_ctas = v; }
   EpiParams ep = epi(EPI_STORE, M, N, bias, out, N, 1);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (block_n == -1) {   // skinny path: needs the (zeroed) split-K scratch
-    REQUIRE(M <= 256 && N % 128 == 0 && K % 64 == 0, "skinny GEMM needs M <= 256, N %% 128 == 0, K %% 64 == 0");
-    CUDA_OK(cudaMalloc(&h.sk_scratch.p, static_cast<size_t>(256) * N * 4)); h.sk_scratch.bytes = static_cast<size_t>(256) * N * 4;
-    CUDA_OK(cudaMalloc(&h.sk_counters.p, 4096)); h.sk_counters.bytes = 4096;
-    CUDA_OK(cudaMemsetAsync(h.sk_scratch.p, 0, h.sk_scratch.bytes, st));
-    CUDA_OK(cudaMemsetAsync(h.sk_counters.p, 0, 4096, st));
-    int rc = gemm_bf16(&h, static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), K, ep, K, st, -1);
-    if (rc == 0) rc = gemm_bf16(&h, static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), K, ep, K, st, -1);   // twice: scratch must be left zeroed
-    cudaStreamSynchronize(st);
-    cudaFree(h.sk_scratch.p); cudaFree(h.sk_counters.p);
-    return rc;
-  }
   return gemm_bf16(&h, static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), K, ep, K, st, block_n);
 }
 

@@ -38,8 +38,17 @@ struct WinGemm {
   int nkb;                  // ceil(K / 64) K blocks
   int pk;                   // K splits; n_ft * pk <= gridDim.x items, item i runs on CTA (i + cta_off) % gridDim.x
   int cta_off;
-  int pad;
+  int a_tiled;              // 1: the activation operand is stored pre-tiled (see win_tiled_off) and fetched with plain bulk copies; tm_a = buffer id
 };
+
+// Operand layout of A1 / A2 / Hm inside the window kernel: [K block][Rp rows][64 bf16] with the 128-byte swizzle of the UMMA
+// descriptor already applied (16-byte chunk index XOR row mod 8), i.e. each K block is the exact shared-memory image of a
+// SW128 K-major tile and is fetched with ONE contiguous cp.async.bulk (measured 165-205 GB/s per SM against ~70 GB/s for
+// the 2D tensor-map load whose rows are 128-byte fragments 2 KB apart).  Rows >= R are never written and stay zero.
+__device__ __forceinline__ size_t win_tiled_off(int r, int c, int Rp) {       // element offset of (row r, column c); c % 4 == 0 keeps 4 elements contiguous
+  const int kb = c >> 6, cc = c & 63;
+  return static_cast<size_t>(kb) * Rp * 64 + static_cast<size_t>(r) * 64 + ((((cc >> 3) ^ (r & 7)) << 3) | (cc & 7));
+}
 
 struct WinParams {
   ModelShape s;
@@ -69,6 +78,11 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                :
                : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -167,7 +181,12 @@ __device__ __forceinline__ void win_gemm_stage(const WinParams& p, const WinGemm
       if (lane == 0) {
         mbar_wait_b(&sm.a_empty[rg.a_slot], rg.a_phase ^ 1, p.err_flag, 1);
         mbar_expect_tx(&sm.a_full[rg.a_slot], a_bytes);
-        tma_load_2d(&p.tmaps[G.tm_a], &sm.a_full[rg.a_slot], sm.aring + rg.a_slot * a_bytes, kb * 64, 0, kEvictLast);
+        if (G.a_tiled) {
+          const __nv_bfloat16* src = (G.tm_a == 0 ? p.A1 : G.tm_a == 1 ? p.A2 : p.Hm) + static_cast<size_t>(kb) * p.Rp * 64;
+          bulk_load_1d(sm.aring + rg.a_slot * a_bytes, src, a_bytes, &sm.a_full[rg.a_slot]);
+        } else {
+          tma_load_2d(&p.tmaps[G.tm_a], &sm.a_full[rg.a_slot], sm.aring + rg.a_slot * a_bytes, kb * 64, 0, kEvictLast);
+        }
       }
       if (++rg.a_slot == NA) { rg.a_slot = 0; rg.a_phase ^= 1; }
     }
@@ -178,8 +197,16 @@ __device__ __forceinline__ void win_gemm_stage(const WinParams& p, const WinGemm
     for (int kb = kb0; kb < kb1; ++kb) {
       if (lane == 0) {
         mbar_wait_b(&sm.w_full[rg.w_slot], rg.w_phase, p.err_flag, 2);
+#ifdef WIN_MARK_DETAIL
+        if (kb == kb0) win_mark(p, epoch, 0);
+#endif
         mbar_wait_b(&sm.a_full[rg.a_slot], rg.a_phase, p.err_flag, 3);
+#ifdef WIN_MARK_DETAIL
+        if (kb == kb0) win_mark(p, epoch, 1);
+        if (kb == kb1 - 1) { atomicAdd(sm.gate, 1); win_mark(p, epoch, 2); }
+#else
         if (kb == kb1 - 1) { atomicAdd(sm.gate, 1); win_mark(p, epoch, 0); }   // quiet point: this stage's operands have landed
+#endif
         tc_fence_after();
         const uint64_t dw = make_sw128_kmajor_desc(smem_u32(sm.wring + rg.w_slot * WIN_W_BYTES));
         const uint64_t da = make_sw128_kmajor_desc(smem_u32(sm.aring + rg.a_slot * a_bytes));
@@ -201,7 +228,11 @@ __device__ __forceinline__ void win_gemm_stage(const WinParams& p, const WinGemm
     mbar_wait_b(sm.t_full, rg.t_phase, p.err_flag, 4);
     rg.t_phase ^= 1;
     tc_fence_after();
+#ifdef WIN_MARK_DETAIL
+    if (issuer) win_mark(p, epoch, 3);
+#else
     if (issuer) win_mark(p, epoch, 1);
+#endif
     const int n_chunks = (p.R + 31) / 32;
     for (int c = 0; c < n_chunks; ++c) {
       float* stg = sm.stg + (c & 1) * (WIN_STG_BYTES / 4);
@@ -222,9 +253,13 @@ __device__ __forceinline__ void win_gemm_stage(const WinParams& p, const WinGemm
       }
     }
     if (issuer) {
+#ifndef WIN_MARK_DETAIL
       win_mark(p, epoch, 2);
+#endif
       bulk_wait<0>();                     // all partial sums are in L2 before this CTA arrives at the grid barrier
+#ifndef WIN_MARK_DETAIL
       win_mark(p, epoch, 3);
+#endif
     }
     tc_fence_before();
   }
@@ -371,7 +406,7 @@ __device__ __noinline__ void win_row_stage(const WinParams& p, float* red_smem, 
       float v[4] = {(x[i].x - mean) * rstd, (x[i].y - mean) * rstd, (x[i].z - mean) * rstd, (x[i].w - mean) * rstd};
 #pragma unroll
       for (int k = 0; k < 4; ++k) v[k] = fmaf(v[k], 1.f + sc[k], sh[k]);
-      *reinterpret_cast<uint2*>(p.A1 + static_cast<size_t>(r) * H + c0 + i * 128) = f32x4_to_bf16(v);
+      *reinterpret_cast<uint2*>(p.A1 + win_tiled_off(r, c0 + i * 128, p.Rp)) = f32x4_to_bf16(v);
     }
     if (WPR > 1) named_bar_sync(3 + grp, WPR * 32);   // red_smem is reused by the next row of this group
   }
@@ -451,7 +486,7 @@ __device__ __noinline__ void win_attn_band5(const WinParams& p, const float* __r
       }
       if (valid[t]) {
         const float inv = __fdividef(1.f, den);
-        __nv_bfloat16* op = p.A2 + static_cast<size_t>(row[t]) * H + hh[t] * hd + lane * VPL;
+        __nv_bfloat16* op = p.A2 + win_tiled_off(row[t], hh[t] * hd + lane * VPL, p.Rp);   // VPL <= 4 elements stay inside one 16-byte chunk
         float o[VPL];
 #pragma unroll
         for (int k = 0; k < VPL; ++k) o[k] = fmaf(acc[k], inv, __ldg(bq + 2 * H + k));   // sum_c p_c (v_c + b) / den = sum_c p_c v_c / den + b
@@ -522,7 +557,7 @@ __device__ __noinline__ void win_attn_wide(const WinParams& p, const float* __re
       }
     }
     const float inv = __fdividef(1.f, den);
-    __nv_bfloat16* op = p.A2 + static_cast<size_t>(row) * H + h * hd + lane * VPL;
+    __nv_bfloat16* op = p.A2 + win_tiled_off(row, h * hd + lane * VPL, p.Rp);
 #pragma unroll
     for (int k = 0; k < VPL; ++k) op[k] = __float2bfloat16_rn(fmaf(acc[k], inv, __ldg(bq + 2 * H + k)));
   }
@@ -558,7 +593,10 @@ __device__ __noinline__ void win_gelu_stage(const WinParams& p, const float* __r
       if (i < total4) {
         if (k == 0) win_mark(p, epoch, 1);
         float v[4] = {gelu_tanh_fast(a[k].x + b[k].x), gelu_tanh_fast(a[k].y + b[k].y), gelu_tanh_fast(a[k].z + b[k].z), gelu_tanh_fast(a[k].w + b[k].w)};
-        *reinterpret_cast<uint2*>(p.Hm + static_cast<size_t>(i) * 4) = f32x4_to_bf16(v);
+        {
+          const unsigned e4 = i * 4, M4u = static_cast<unsigned>(M4);
+          *reinterpret_cast<uint2*>(p.Hm + win_tiled_off(static_cast<int>(e4 / M4u), static_cast<int>(e4 % M4u), p.Rp)) = f32x4_to_bf16(v);
+        }
         *reinterpret_cast<float4*>(p.Hacc + static_cast<size_t>(i) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }

@@ -57,25 +57,6 @@ def test_cta_pair_gemm_matches_torch(lib, M, N, K, block_n):
     assert err <= 4e-3 * max(1.0, ref.abs().max().item()), err
 
 
-@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
-@pytest.mark.parametrize("M,N,K", [(180, 3072, 1024), (180, 1024, 4096), (60, 1024, 512), (240, 512, 1024), (180, 1024, 1088), (256, 4096, 1024), (17, 128, 64)])
-def test_skinny_gemm_matches_torch(lib, M, N, K, cluster, monkeypatch):
-    """Weight-stationary skinny-M GEMM: split-K with RED atomics + last-CTA fix-up, TMA multicast over clusters."""
-    L, cabi = lib
-    monkeypatch.setenv("FMT_SK_CLUSTER", str(cluster))
-    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
-    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
-    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
-    bias = torch.randn(N, device="cuda", generator=g)
-    out = torch.full((M, N), float("nan"), device="cuda")
-    cabi.check(L.fmt_debug_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, -1, _stream()), "gemm")
-    torch.cuda.synchronize()
-    ref = A.double() @ W.double().t() + bias.double()
-    err = (out.double() - ref).abs().max().item()
-    assert torch.isfinite(out).all()
-    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), err
-
-
 @pytest.mark.parametrize("M,N,K", [(180, 3072, 1024), (70, 68, 64), (360, 512, 1088)])
 def test_fp32_simt_gemm_matches_torch(lib, M, N, K):
     L, cabi = lib

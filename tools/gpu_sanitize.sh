@@ -1,0 +1,7 @@
+#!/bin/bash
+# compute-sanitizer over the small-architecture parity cases (window kernel, per-op kernels) - memcheck + racecheck
+mkdir -p gpurun_out
+timeout -s KILL 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "small_static or small_dynamic or small_rcfg" > gpurun_out/sanitize_memcheck.log 2>&1
+echo "memcheck exit $?"; tail -6 gpurun_out/sanitize_memcheck.log
+timeout -s KILL 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "bf16_mode and small_static" > gpurun_out/sanitize_racecheck.log 2>&1
+echo "racecheck exit $?"; tail -6 gpurun_out/sanitize_racecheck.log
