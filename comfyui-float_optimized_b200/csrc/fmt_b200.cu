@@ -90,8 +90,12 @@ struct FmtHandle {
   size_t ws_bytes = 0;
 
   // persistent window kernel (window.cuh): used when the plan has <= 256 token rows in bf16 mode
-  bool use_window = true;                        // FMT_WINDOW=0 disables (falls back to one kernel per op)
+  int use_window = 1;                            // FMT_WINDOW: 0 = one kernel per op, 1 = split-K window kernel, 2 = grouped window kernel
   bool window_active = false;
+  bool win_grouped = false;                      // the active plan runs fmt_window_kernel<NV, true>
+  int win_spg = 1;                               // sequences per group (FMT_WIN_SPG), rows per group = spg * N <= 128
+  int win_fuse_gelu = 1;                         // FMT_WIN_FUSE_GELU=0 keeps the separate GELU stage in the grouped schedule
+  int win_nf[4] = {0, 0, 0, 0};                  // feature-slice overrides for qkv / proj / fc1 / fc2 (FMT_WIN_NF; 0 = auto)
   int win_pk[4] = {0, 0, 0, 0};                  // K-split overrides for qkv / proj / fc1 / fc2 (FMT_WIN_PK="q,p,1,2"; 0 = auto)
   DevBuf win_params, win_tmaps, win_acc, win_bar, win_trace, win_act;   // win_act: pre-tiled A1 | A2 | Hm operands
   int win_trace_stride = 0;
@@ -396,7 +400,7 @@ static bool window_eligible(const FmtHandle* h, const FmtPlan* p) {
   const FmtDims& d = h->d;
   const int R = p->n_branches * p->batch * (d.num_prev_frames + d.frames_per_clip);
   const int nv = d.dim_h / 128;
-  return h->use_window && p->mode == FMT_MODE_BF16 && R <= 256 && p->n_steps * p->n_stages >= 1 && d.depth <= WIN_MAX_DEPTH &&
+  return h->use_window != 0 && p->mode == FMT_MODE_BF16 && R <= 256 && p->n_steps * p->n_stages >= 1 && d.depth <= WIN_MAX_DEPTH &&
          (nv == 1 || nv == 2 || nv == 4 || nv == 8) && d.mlp_hidden % 64 == 0 && d.dim_w % 64 == 0;
 }
 
@@ -406,17 +410,27 @@ static int setup_window(FmtHandle* h, cudaStream_t st) {
   const ModelShape& s = h->shape;
   const FmtDims& d = h->d;
   const int R = h->R, H = s.H, M4 = d.mlp_hidden, W = s.W, D = d.depth;
-  const int Rp = R <= 64 ? 64 : R <= 128 ? 128 : R <= 192 ? 192 : 256;
+  int Rp = R <= 64 ? 64 : R <= 128 ? 128 : R <= 192 ? 192 : 256;
   const int n_gemms = 2 + 4 * D;
   const int grid = h->num_sms;
   WinParams wp{};
+  // grouped schedule: groups of whole sequences (<= 128 rows each), one slice of the SMs per group
+  const int n_seq = s.nb * s.B;
+  int spg = h->win_spg >= 1 ? h->win_spg : 1;
+  if (n_seq % spg != 0 || spg * s.N > 128) spg = 1;
+  const bool grouped = h->use_window == 2 && s.N * spg <= 128 && H % 16 == 0 && M4 % 16 == 0 && W % 16 == 0 && grid / (n_seq / spg) >= 8;
+  h->win_grouped = grouped;
+  if (grouped) {
+    wp.G = n_seq / spg; wp.Cg = grid / wp.G; wp.Rg = spg * s.N; wp.RgP = wp.Rg <= 64 ? 64 : 128;
+    Rp = wp.G * wp.RgP;                                   // G pre-tiled buffers of RgP rows each
+  }
   wp.s = s; wp.R = R; wp.Rp = Rp; wp.depth = D; wp.heads = d.num_heads; wp.window = d.attention_window; wp.mlp_hidden = M4; wp.NT = h->NT;
   wp.n_steps = h->plan.n_steps; wp.n_stages = h->plan.n_stages; wp.n_gemms = n_gemms;
 
   // accumulator arena: [Pacc (R,H) | QKVacc (R,3H) | Hacc (R,M4) | Vacc (R,W)] fp32, zeroed by one memset per window
   const size_t n_p = static_cast<size_t>(R) * H, n_q = static_cast<size_t>(R) * 3 * H, n_h = static_cast<size_t>(R) * M4, n_v = static_cast<size_t>(R) * W;
   FMT_OK(dev_alloc(h, h->win_acc, (n_p + n_q + n_h + n_v) * 4));
-  FMT_OK(dev_alloc(h, h->win_bar, 256));
+  FMT_OK(dev_alloc(h, h->win_bar, 2048));                 // [0]: grid barrier, [32 * (1 + g)]: barrier of group g (one 128-byte line each)
   FMT_OK(dev_alloc(h, h->win_params, sizeof(WinParams)));
   const int n_maps = n_gemms + 8;
   FMT_OK(dev_alloc(h, h->win_tmaps, static_cast<size_t>(n_maps) * sizeof(CUtensorMap)));
@@ -445,8 +459,9 @@ static int setup_window(FmtHandle* h, cudaStream_t st) {
   wp.tmaps = static_cast<const CUtensorMap*>(h->win_tmaps.p);
   wp.w_lookahead = 1;
   if (const char* e = getenv("FMT_WIN_LA")) wp.w_lookahead = atoi(e);
+  if (const char* e = getenv("FMT_WIN_DBG")) wp.dbg = atoi(e);
   if (getenv("FMT_WIN_TRACE") && atoi(getenv("FMT_WIN_TRACE")) != 0) {
-    h->win_trace_stride = h->n_eval * (4 + 8 * D);
+    h->win_trace_stride = h->n_eval * (4 + 8 * D);       // upper bound (the grouped schedule with the fused GELU has 4 + 7 * D stages)
     FMT_OK(dev_alloc(h, h->win_trace, static_cast<size_t>(grid) * h->win_trace_stride * 6 * sizeof(long long)));
     CUDA_OK(cudaMemsetAsync(h->win_trace.p, 0, h->win_trace.bytes, st));
     wp.trace = static_cast<long long*>(h->win_trace.p); wp.trace_stride = h->win_trace_stride;
@@ -456,7 +471,7 @@ static int setup_window(FmtHandle* h, cudaStream_t st) {
   const int A_AX = n_gemms, A_A1 = n_gemms + 1, A_A2 = n_gemms + 2, A_HM = n_gemms + 3;
   const int C_P = n_gemms + 4, C_Q = n_gemms + 5, C_H = n_gemms + 6, C_V = n_gemms + 7;
   const CUtensorMapDataType BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  FMT_OK(make_tmap_ex(h, &maps[A_AX], wp.ax, BF, 2, R, W, W, 64, Rp, CU_TENSOR_MAP_SWIZZLE_128B));
+  FMT_OK(make_tmap_ex(h, &maps[A_AX], wp.ax, BF, 2, R, W, W, 64, grouped ? wp.RgP : Rp, CU_TENSOR_MAP_SWIZZLE_128B));
   maps[A_A1] = maps[A_AX]; maps[A_A2] = maps[A_AX]; maps[A_HM] = maps[A_AX];   // A1 / A2 / Hm are pre-tiled: fetched with bulk copies, no tensor map
   FMT_OK(make_tmap_ex(h, &maps[C_P], wp.Pacc, F32, 4, R, H, H, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
   FMT_OK(make_tmap_ex(h, &maps[C_Q], wp.QKVacc, F32, 4, R, 3 * H, 3 * H, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
@@ -480,37 +495,79 @@ static int setup_window(FmtHandle* h, cudaStream_t st) {
     next_off = (next_off + G.n_ft * pk) % grid;
     return make_tmap_ex(h, &maps[g], L.w16, BF, 2, L.N, L.K, L.K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
   };
-  FMT_OK(plan_gemm(0, h->x_emb, A_AX, C_P, 0));
-  for (int i = 0; i < D; ++i) {
-    FMT_OK(plan_gemm(1 + 4 * i, h->qkv[i], A_A1, C_Q, h->win_pk[0]));
-    FMT_OK(plan_gemm(2 + 4 * i, h->proj[i], A_A2, C_P, h->win_pk[1]));
-    FMT_OK(plan_gemm(3 + 4 * i, h->fc1[i], A_A1, C_H, h->win_pk[2]));
-    FMT_OK(plan_gemm(4 + 4 * i, h->fc2[i], A_HM, C_P, h->win_pk[3]));
+  // grouped schedule: slice the output features over the CTAs of a group; K is split only where one CTA would otherwise
+  // have to pull the whole K = mlp_hidden operand (fc2)
+  auto plan_gemm2 = [&](int g, const Linear& L, int tm_a, int out, int pk_override, int nf_override, int epi) -> int {
+    WinGemm& G = wp.gemms[g];
+    G.tm_w = g; G.tm_a = tm_a; G.tm_acc = 0; G.out = out; G.N = L.N;
+    G.a_tiled = 0;
+    if (tm_a == A_A1 || tm_a == A_A2 || tm_a == A_HM) { G.a_tiled = 1; G.tm_a = tm_a == A_A1 ? 0 : tm_a == A_A2 ? 1 : 2; }
+    G.nkb = (L.K + 63) / 64;
+    REQUIRE(L.N % 16 == 0, "window kernel: N = %d is not a multiple of 16", L.N);
+    int pk = pk_override > 0 ? pk_override : (L.K >= 3072 ? 3 : 1);
+    if (pk > G.nkb) pk = G.nkb;
+    if (pk > 8) pk = 8;
+    int nf = 0;
+    for (;;) {                                            // smallest slice that covers N with Cg / pk CTAs, at most 128 wide
+      const int slots = wp.Cg / pk;
+      nf = slots > 0 ? ((L.N + slots - 1) / slots + 15) / 16 * 16 : 1 << 30;
+      for (int c : {16, 32, 48, 64, 96, 128})                // slice widths that pack a 24 KB ring slot (192 / nf K blocks) without waste
+        if (nf <= c) { nf = c; break; }
+      if (nf <= 128) break;
+      REQUIRE(pk > 1, "window kernel: N = %d does not fit %d CTAs per group", L.N, wp.Cg);
+      --pk;
+    }
+    if (nf_override >= 16 && nf_override <= 128 && nf_override % 16 == 0 && ((L.N + nf_override - 1) / nf_override) * pk <= wp.Cg) nf = nf_override;
+    G.nf = nf; G.n_nt = (L.N + nf - 1) / nf; G.pk = pk; G.n_ft = G.n_nt;
+    G.epi = (epi == 1 && pk == 1) ? 1 : 0;
+    G.cta_off = next_off;
+    next_off = (next_off + G.n_nt * pk) % wp.Cg;
+    return make_tmap_ex(h, &maps[g], L.w16, BF, 2, L.N, L.K, L.K, 64, nf, CU_TENSOR_MAP_SWIZZLE_128B);
+  };
+  if (grouped) {
+    FMT_OK(plan_gemm2(0, h->x_emb, A_AX, 0, 0, 0, 0));
+    for (int i = 0; i < D; ++i) {
+      FMT_OK(plan_gemm2(1 + 4 * i, h->qkv[i], A_A1, 1, h->win_pk[0], h->win_nf[0], 0));
+      FMT_OK(plan_gemm2(2 + 4 * i, h->proj[i], A_A2, 0, h->win_pk[1], h->win_nf[1], 0));
+      FMT_OK(plan_gemm2(3 + 4 * i, h->fc1[i], A_A1, 2, h->win_pk[2], h->win_nf[2], h->win_fuse_gelu));
+      FMT_OK(plan_gemm2(4 + 4 * i, h->fc2[i], A_HM, 0, h->win_pk[3], h->win_nf[3], 0));
+    }
+    FMT_OK(plan_gemm2(1 + 4 * D, h->dec, A_A1, 3, 0, 0, 0));
+    wp.fuse_gelu = wp.gemms[3].epi;
+  } else {
+    FMT_OK(plan_gemm(0, h->x_emb, A_AX, C_P, 0));
+    for (int i = 0; i < D; ++i) {
+      FMT_OK(plan_gemm(1 + 4 * i, h->qkv[i], A_A1, C_Q, h->win_pk[0]));
+      FMT_OK(plan_gemm(2 + 4 * i, h->proj[i], A_A2, C_P, h->win_pk[1]));
+      FMT_OK(plan_gemm(3 + 4 * i, h->fc1[i], A_A1, C_H, h->win_pk[2]));
+      FMT_OK(plan_gemm(4 + 4 * i, h->fc2[i], A_HM, C_P, h->win_pk[3]));
+    }
+    FMT_OK(plan_gemm(1 + 4 * D, h->dec, A_A1, C_V, 0));
   }
-  FMT_OK(plan_gemm(1 + 4 * D, h->dec, A_A1, C_V, 0));
   CUDA_OK(cudaMemcpyAsync(h->win_tmaps.p, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemcpyAsync(h->win_params.p, &wp, sizeof(WinParams), cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaStreamSynchronize(st));   // `maps` / `wp` are stack objects
   return 0;
 }
 
-template <int NV>
+template <int NV, bool GROUPED>
 static int launch_window_nv(FmtHandle* h, cudaStream_t st) {
+  constexpr int SMEM = GROUPED ? WIN2_SMEM_BYTES : WIN_SMEM_BYTES;
   static bool attr_set[64] = {};
   if (!attr_set[h->device & 63]) {
-    CUDA_OK(cudaFuncSetAttribute(fmt_window_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fmt_window_kernel<NV, GROUPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set[h->device & 63] = true;
   }
   int occ = 0;
-  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fmt_window_kernel<NV>, WIN_THREADS, WIN_SMEM_BYTES));
-  REQUIRE(occ >= 1, "window kernel does not fit on an SM (%d B smem)", WIN_SMEM_BYTES);
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fmt_window_kernel<NV, GROUPED>, WIN_THREADS, SMEM));
+  REQUIRE(occ >= 1, "window kernel does not fit on an SM (%d B smem)", SMEM);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(h->num_sms); cfg.blockDim = dim3(WIN_THREADS); cfg.dynamicSmemBytes = WIN_SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = dim3(h->num_sms); cfg.blockDim = dim3(WIN_THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
   cudaLaunchAttribute attrs[1];
   attrs[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: the kernel synchronises across the grid
   attrs[0].val.cooperative = 1;
   cfg.attrs = attrs; cfg.numAttrs = 1;
-  CUDA_OK(cudaLaunchKernelEx(&cfg, fmt_window_kernel<NV>, static_cast<const WinParams*>(h->win_params.p)));
+  CUDA_OK(cudaLaunchKernelEx(&cfg, fmt_window_kernel<NV, GROUPED>, static_cast<const WinParams*>(h->win_params.p)));
   count_launch(h);
   return 0;
 }
@@ -519,10 +576,10 @@ static int launch_window(FmtHandle* h, cudaStream_t st) {
   CUDA_OK(cudaMemsetAsync(h->win_acc.p, 0, h->win_acc.bytes, st));
   CUDA_OK(cudaMemsetAsync(h->win_bar.p, 0, h->win_bar.bytes, st));
   switch (h->shape.H / 128) {
-    case 1: return launch_window_nv<1>(h, st);
-    case 2: return launch_window_nv<2>(h, st);
-    case 4: return launch_window_nv<4>(h, st);
-    case 8: return launch_window_nv<8>(h, st);
+    case 1: return h->win_grouped ? launch_window_nv<1, true>(h, st) : launch_window_nv<1, false>(h, st);
+    case 2: return h->win_grouped ? launch_window_nv<2, true>(h, st) : launch_window_nv<2, false>(h, st);
+    case 4: return h->win_grouped ? launch_window_nv<4, true>(h, st) : launch_window_nv<4, false>(h, st);
+    case 8: return h->win_grouped ? launch_window_nv<8, true>(h, st) : launch_window_nv<8, false>(h, st);
   }
   return set_err(-1, "window kernel: dim_h %d unsupported", h->shape.H);
 }
@@ -648,7 +705,10 @@ int32_t fmt_create(const FmtDims* dims, const void* const* wp, int32_t n_ptrs, i
   h->Kc = ((d.dim_w + d.dim_a + d.dim_e + 63) / 64) * 64;
   h->NT = d.depth * 6 * d.dim_h + 2 * d.dim_h;
   if (const char* e = getenv("FMT_PDL")) h->use_pdl = atoi(e) != 0;
-  if (const char* e = getenv("FMT_WINDOW")) h->use_window = atoi(e) != 0;
+  if (const char* e = getenv("FMT_WINDOW")) h->use_window = atoi(e);
+  if (const char* e = getenv("FMT_WIN_SPG")) h->win_spg = atoi(e);
+  if (const char* e = getenv("FMT_WIN_FUSE_GELU")) h->win_fuse_gelu = atoi(e) != 0;
+  if (const char* e = getenv("FMT_WIN_NF")) sscanf(e, "%d,%d,%d,%d", &h->win_nf[0], &h->win_nf[1], &h->win_nf[2], &h->win_nf[3]);
   if (const char* e = getenv("FMT_PAIR")) h->use_pair = atoi(e) != 0;
   if (const char* e = getenv("FMT_SPLITK")) h->use_splitk = atoi(e) != 0;
   if (const char* e = getenv("FMT_RASTER_GM")) { int v = atoi(e); if (v >= 1) h->raster_gm = v; }
@@ -855,14 +915,14 @@ int32_t fmt_configure(FmtHandle* h, const FmtPlan* p, void* stream) {
     int occ = 0;
     cudaError_t oe = cudaErrorUnknown;
     switch (d.dim_h / 128) {
-      case 1: oe = cudaFuncSetAttribute(fmt_window_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM_BYTES);
-              if (oe == cudaSuccess) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fmt_window_kernel<1>, WIN_THREADS, WIN_SMEM_BYTES); break;
-      case 2: oe = cudaFuncSetAttribute(fmt_window_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM_BYTES);
-              if (oe == cudaSuccess) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fmt_window_kernel<2>, WIN_THREADS, WIN_SMEM_BYTES); break;
-      case 4: oe = cudaFuncSetAttribute(fmt_window_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM_BYTES);
-              if (oe == cudaSuccess) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fmt_window_kernel<4>, WIN_THREADS, WIN_SMEM_BYTES); break;
-      case 8: oe = cudaFuncSetAttribute(fmt_window_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM_BYTES);
-              if (oe == cudaSuccess) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fmt_window_kernel<8>, WIN_THREADS, WIN_SMEM_BYTES); break;
+      case 1: oe = cudaFuncSetAttribute(fmt_window_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM_BYTES);
+              if (oe == cudaSuccess) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fmt_window_kernel<1, false>, WIN_THREADS, WIN_SMEM_BYTES); break;
+      case 2: oe = cudaFuncSetAttribute(fmt_window_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM_BYTES);
+              if (oe == cudaSuccess) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fmt_window_kernel<2, false>, WIN_THREADS, WIN_SMEM_BYTES); break;
+      case 4: oe = cudaFuncSetAttribute(fmt_window_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM_BYTES);
+              if (oe == cudaSuccess) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fmt_window_kernel<4, false>, WIN_THREADS, WIN_SMEM_BYTES); break;
+      case 8: oe = cudaFuncSetAttribute(fmt_window_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM_BYTES);
+              if (oe == cudaSuccess) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fmt_window_kernel<8, false>, WIN_THREADS, WIN_SMEM_BYTES); break;
     }
     if (oe != cudaSuccess || occ < 1) { (void)cudaGetLastError(); h->window_active = false; }
   }

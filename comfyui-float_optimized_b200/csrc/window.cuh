@@ -29,6 +29,18 @@ constexpr int WIN_MAX_NA = 8;
 constexpr int WIN_STG_BYTES = 32 * 128 * 4;      // epilogue staging: 32 rows x 128 features fp32
 constexpr int WIN_BAR_BYTES = 512;
 constexpr int WIN_SMEM_BYTES = WIN_NW * WIN_W_BYTES + WIN_A_RING + 2 * WIN_STG_BYTES + WIN_BAR_BYTES + 1024;
+// grouped schedule: every CTA pulls 1/Cg (not 1/148) of a layer's weights plus the whole operand of its group per stage, and the
+// rate of that pull is (bytes in flight) / (L2 or HBM latency): the rings take all of shared memory and a weight slot holds
+// several K blocks (24 KB / (nf * 128 B)), so ~144 KB of weights are requested before the stage starts
+// Slots hold SEVERAL K blocks (weights: 24 KB / (nf * 128 B); activations: 32 KB / (RgP * 128 B)): a slot is handed back with
+// ONE tcgen05.commit, and commits are the expensive part of the hand-off (measured: a loop that commits twice per K block
+// paces at ~0.45 us per K block with no loads and no MMAs in flight).
+constexpr int WIN2_NW = 4;
+constexpr int WIN2_W_BYTES = 24 * 1024;
+constexpr int WIN2_NA = 3;
+constexpr int WIN2_A_BYTES = 32 * 1024;          // 4 K blocks of a 64-row group, 2 of a 128-row group
+constexpr int WIN2_A_RING = WIN2_NA * WIN2_A_BYTES + 8 * 1024;   // + 8 KB the M = 128 descriptor of the last K block reaches into when RgP = 64
+constexpr int WIN2_SMEM_BYTES = WIN2_NW * WIN2_W_BYTES + WIN2_A_RING + WIN_BAR_BYTES + 1024;
 constexpr int WIN_MAX_DEPTH = 16;
 constexpr int WIN_MAX_GEMMS = 2 + 4 * WIN_MAX_DEPTH;
 
@@ -39,6 +51,12 @@ struct WinGemm {
   int pk;                   // K splits; n_ft * pk <= gridDim.x items, item i runs on CTA (i + cta_off) % gridDim.x
   int cta_off;
   int a_tiled;              // 1: the activation operand is stored pre-tiled (see win_tiled_off) and fetched with plain bulk copies; tm_a = buffer id
+  // grouped schedule (fmt_window_kernel<NV, true>): item = nf output features x a range of K blocks, one item per CTA of a group
+  int nf;                   // output features per item (multiple of 16, <= 128) = UMMA N
+  int n_nt;                 // ceil(N / nf) feature slices
+  int N;                    // output features of the layer
+  int out;                  // 0: Pacc, 1: QKVacc, 2: Hacc, 3: Vacc
+  int epi;                  // 0: accumulator (+)= partial; 1: Hm = bf16(GELU(acc + bias)) (fc1 with pk == 1: the GELU stage is skipped)
 };
 
 // Operand layout of A1 / A2 / Hm inside the window kernel: [K block][Rp rows][64 bf16] with the 128-byte swizzle of the UMMA
@@ -70,6 +88,21 @@ struct WinParams {
   long long* trace;                    // optional (FMT_WIN_TRACE=1): [cta][barrier][6] SM-clock stamps (arrive, pass, 4 intra-stage marks of the NEXT stage)
   int trace_stride;                    // barriers per CTA recorded
   int w_lookahead;                     // weight prefetch may run this many stages ahead of the stage in flight (>= 1000: ungated)
+  // grouped schedule: G groups of Cg CTAs, group g owns token rows [g * Rg, (g + 1) * Rg) (whole sequences) and its own
+  // pre-tiled operand buffers of RgP (64 or 128) rows; bar_counter[32 * (1 + g)] is the group's barrier, bar_counter[0] the global one
+  int G, Cg, Rg, RgP;
+  int fuse_gelu;                       // 1: fc1's epilogue writes Hm, evaluation has 4 + 7 * depth stages
+  int dbg;                             // timing experiments only (FMT_WIN_DBG; results are wrong when set): 1 = no MMAs, 2 = no activation loads, 4 = no weight loads
+};
+
+// What a CTA works on in the SIMT stages: all rows / all CTAs in the split-K schedule, one group's rows / CTAs in the grouped one.
+struct WinCtx {
+  int row0, nrows;                     // token rows [row0, row0 + nrows)
+  int rank, nranks;                    // this CTA among the CTAs sharing those rows
+  int all_rank, all_n;                 // this CTA among all working CTAs (COMB stage)
+  int RgP;                             // padded rows of the pre-tiled operand buffers below
+  __nv_bfloat16 *A1, *A2, *Hm;         // this group's pre-tiled operands (local row = r - row0)
+  unsigned* bar;                       // the barrier counter shared by `nranks` CTAs
 };
 
 // ---------------------------------------------------------------- small PTX helpers local to this kernel
@@ -126,10 +159,12 @@ struct WinSmem {
   uint64_t *w_full, *w_empty, *a_full, *a_empty, *t_full;
   uint32_t* tmem_slot;
   int* gate;          // quiet points passed (see win_weight_producer)
+  int nw, w_bytes;    // weight ring: slots, bytes per slot
 };
 
-// grid barrier for the main group (256 threads, named barrier 1); `epoch` counts barriers passed
-__device__ __forceinline__ void win_grid_sync(const WinParams& p, unsigned& epoch) {
+// barrier over the CTAs that share `counter` (the whole grid, or one group), entered by the main group (256 threads, named
+// barrier 1); `epoch` counts the barriers this CTA has passed (trace index), `target` = arrivals that complete this one
+__device__ __forceinline__ void win_grid_sync(const WinParams& p, unsigned& epoch, unsigned* counter, unsigned target) {
   fence_proxy_async_all();                 // this thread's generic-proxy writes -> visible to later TMA (async proxy) reads
   named_bar_sync(1, WIN_MAIN);
   ++epoch;
@@ -137,10 +172,9 @@ __device__ __forceinline__ void win_grid_sync(const WinParams& p, unsigned& epoc
     long long* tr = (p.trace != nullptr && static_cast<int>(epoch) <= p.trace_stride)
                         ? p.trace + (static_cast<size_t>(blockIdx.x) * p.trace_stride + (epoch - 1)) * 6 : nullptr;
     if (tr) tr[0] = clock64();
-    red_release_gpu_add(p.bar_counter, 1u);
-    const unsigned target = epoch * gridDim.x;
+    red_release_gpu_add(counter, 1u);
     const long long t0 = clock64();
-    while (ld_acquire_gpu(p.bar_counter) < target) {
+    while (ld_acquire_gpu(counter) < target) {
       if (clock64() - t0 > WIN_SPIN_LIMIT) win_fail(p.err_flag, 100 + static_cast<int>(epoch & 0xffff));
     }
     if (tr) tr[1] = clock64();
@@ -165,14 +199,18 @@ struct WinRing {   // ring position kept identically by every lane of a role war
   uint32_t t_phase = 0;
 };
 
+// This CTA's item of every GEMM, computed once at kernel start (the integer divisions of win_item / win_item2 cost ~0.5 us per
+// stage when a single warp executes them on the critical path): x = feature tile / slice (-1: no item), y = first K block, z = end
+struct WinItems { int4 it[WIN_MAX_GEMMS]; };
+
 // ---------------------------------------------------------------------------------------------------------------- GEMM
-__device__ __forceinline__ void win_gemm_stage(const WinParams& p, const WinGemm& G, const WinSmem& sm, WinRing& rg, int NA,
+__device__ __forceinline__ void win_gemm_stage(const WinParams& p, const WinGemm& G, const int4 item, const WinSmem& sm, WinRing& rg, int NA,
                                                uint32_t tmem_base, unsigned epoch) {
-  int ft, kb0, kb1;
-  if (!win_item(G, ft, kb0, kb1)) {
-    if (threadIdx.x == 32) atomicAdd(sm.gate, 1);
+  if (item.x < 0) {
+    if (threadIdx.x == 32) atomicAdd_block(sm.gate, 1);
     return;
   }
+  const int ft = item.x, kb0 = item.y, kb1 = item.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, mw = warp - 1;
   const int a_bytes = p.Rp * 128;
   if (mw == 0) {
@@ -193,46 +231,46 @@ __device__ __forceinline__ void win_gemm_stage(const WinParams& p, const WinGemm
     __syncwarp();
   } else if (mw == 1) {
     // ===================== MMA issuer =====================
+    // warp-uniform loop (every lane waits, one elected lane issues) with a small body: a single warp runs dependent
+    // instructions at ~5 cycles each, so at 4 MMAs per K block the instruction count of this loop paces the stage
     const uint32_t idesc = make_idesc_bf16_f32(128, static_cast<uint32_t>(p.Rp));
+    const uint64_t desc_hi = make_sw128_kmajor_desc(0);
+    const uint32_t w_base = smem_u32(sm.wring) >> 4, a_base = smem_u32(sm.aring) >> 4, ab16 = a_bytes >> 4;
+    const bool leader = elect_one();
+    int w_slot = rg.w_slot, a_slot = rg.a_slot;
+    uint32_t w_phase = rg.w_phase, a_phase = rg.a_phase;
+    uint32_t accum = 0;
     for (int kb = kb0; kb < kb1; ++kb) {
-      if (lane == 0) {
-        mbar_wait_b(&sm.w_full[rg.w_slot], rg.w_phase, p.err_flag, 2);
-#ifdef WIN_MARK_DETAIL
-        if (kb == kb0) win_mark(p, epoch, 0);
-#endif
-        mbar_wait_b(&sm.a_full[rg.a_slot], rg.a_phase, p.err_flag, 3);
-#ifdef WIN_MARK_DETAIL
-        if (kb == kb0) win_mark(p, epoch, 1);
-        if (kb == kb1 - 1) { atomicAdd(sm.gate, 1); win_mark(p, epoch, 2); }
-#else
-        if (kb == kb1 - 1) { atomicAdd(sm.gate, 1); win_mark(p, epoch, 0); }   // quiet point: this stage's operands have landed
-#endif
-        tc_fence_after();
-        const uint64_t dw = make_sw128_kmajor_desc(smem_u32(sm.wring + rg.w_slot * WIN_W_BYTES));
-        const uint64_t da = make_sw128_kmajor_desc(smem_u32(sm.aring + rg.a_slot * a_bytes));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, dw + 2 * k, da + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-        umma_commit(&sm.w_empty[rg.w_slot]);
-        umma_commit(&sm.a_empty[rg.a_slot]);
-        if (kb == kb1 - 1) umma_commit(sm.t_full);
+      mbar_wait_b(&sm.w_full[w_slot], w_phase, p.err_flag, 2);
+      mbar_wait_b(&sm.a_full[a_slot], a_phase, p.err_flag, 3);
+      tc_fence_after();
+      if (leader) {
+        const bool last = kb == kb1 - 1;
+        const uint64_t dw = desc_hi | (w_base + w_slot * (WIN_W_BYTES >> 4)), da = desc_hi | (a_base + a_slot * ab16);
+        umma_bf16(tmem_base, dw, da, idesc, accum);
+        umma_bf16(tmem_base, dw + 2, da + 2, idesc, 1u);
+        umma_bf16(tmem_base, dw + 4, da + 4, idesc, 1u);
+        umma_bf16(tmem_base, dw + 6, da + 6, idesc, 1u);
+        umma_commit(&sm.w_empty[w_slot]);
+        umma_commit(&sm.a_empty[a_slot]);
+        if (last) { umma_commit(sm.t_full); atomicAdd_block(sm.gate, 1); win_mark(p, epoch, 0); }   // quiet point: this stage's operands have landed
       }
-      if (++rg.w_slot == WIN_NW) { rg.w_slot = 0; rg.w_phase ^= 1; }
-      if (++rg.a_slot == NA) { rg.a_slot = 0; rg.a_phase ^= 1; }
+      accum = 1u;
+      if (++w_slot == WIN_NW) { w_slot = 0; w_phase ^= 1; }
+      if (++a_slot == NA) { a_slot = 0; a_phase ^= 1; }
     }
+    rg.w_slot = w_slot; rg.w_phase = w_phase; rg.a_slot = a_slot; rg.a_phase = a_phase;
     __syncwarp();
   } else if (mw >= 4) {
     // ===================== epilogue: TMEM (lanes = features, columns = rows) -> smem [row][feature] -> TMA reduce-add
     const int quarter = warp & 3;
     const int fl = quarter * 32 + lane;
     const bool issuer = (mw == 4 && lane == 0);
-    mbar_wait_b(sm.t_full, rg.t_phase, p.err_flag, 4);
+    if (lane == 0) mbar_wait_b(sm.t_full, rg.t_phase, p.err_flag, 4);      // one poller per warp
+    __syncwarp();
     rg.t_phase ^= 1;
     tc_fence_after();
-#ifdef WIN_MARK_DETAIL
-    if (issuer) win_mark(p, epoch, 3);
-#else
     if (issuer) win_mark(p, epoch, 1);
-#endif
     const int n_chunks = (p.R + 31) / 32;
     for (int c = 0; c < n_chunks; ++c) {
       float* stg = sm.stg + (c & 1) * (WIN_STG_BYTES / 4);
@@ -253,15 +291,192 @@ __device__ __forceinline__ void win_gemm_stage(const WinParams& p, const WinGemm
       }
     }
     if (issuer) {
-#ifndef WIN_MARK_DETAIL
       win_mark(p, epoch, 2);
-#endif
       bulk_wait<0>();                     // all partial sums are in L2 before this CTA arrives at the grid barrier
-#ifndef WIN_MARK_DETAIL
       win_mark(p, epoch, 3);
-#endif
     }
     tc_fence_before();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- GEMM, grouped schedule
+// Group g (Cg CTAs) owns whole sequences: <= 128 token rows.  Roles are swapped with respect to the split-K schedule: the
+// group's activation tile [RgP rows x 64 K] is the UMMA A operand (M = 128; with RgP = 64 the upper 64 lanes read whatever
+// follows in the ring and are never looked at), the weight slice [nf features x 64 K] is the B operand (N = nf), so the
+// output features of a layer are dealt to the CTAs of the group in slices of nf (a multiple of 16, not of 128) and K is
+// split at most pk <= 4 ways.  The fp32 tile D[row = TMEM lane, feature = column] leaves through registers: pk == 1 ->
+// plain 256-bit stores (or the fused GELU -> bf16 operand), pk > 1 -> red.global.add.v4.f32 (64 rows x nf x 4 B per CTA).
+__device__ __forceinline__ bool win_item2(const WinGemm& G, const WinCtx& cx, int& nt, int& kb0, int& kb1) {
+  int item = cx.rank - G.cta_off;
+  if (item < 0) item += cx.nranks;
+  if (item >= G.n_nt * G.pk) return false;
+  nt = item % G.n_nt;
+  const int ks = item / G.n_nt;
+  kb0 = ks * G.nkb / G.pk;
+  kb1 = (ks + 1) * G.nkb / G.pk;
+  return kb1 > kb0;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x);
+
+__device__ __forceinline__ void win_gemm2_stage(const WinParams& p, const WinCtx& cx, const WinGemm& G, const int4 item, const WinSmem& sm, WinRing& rg,
+                                                uint32_t tmem_base, unsigned epoch, const float* __restrict__ bias) {
+  if (item.x < 0) {
+    if (threadIdx.x == 32) atomicAdd_block(sm.gate, 1);
+    return;
+  }
+  const int nt = item.x, kb0 = item.y, kb1 = item.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, mw = warp - 1;
+  const int a_bytes = cx.RgP * 128;
+  if (mw == 0) {
+    // ===================== activation producer: this group's K blocks kb0..kb1 of the operand, kpa per ring slot =====================
+    const int kpa = WIN2_A_BYTES / a_bytes;
+    for (int kb = kb0; kb < kb1; kb += kpa) {
+      const int n = min(kpa, kb1 - kb);
+      if (lane == 0) {
+        uint8_t* dst = sm.aring + rg.a_slot * WIN2_A_BYTES;
+        mbar_wait_b(&sm.a_empty[rg.a_slot], rg.a_phase ^ 1, p.err_flag, 1);
+        mbar_expect_tx(&sm.a_full[rg.a_slot], n * a_bytes);
+        if (G.a_tiled) {      // consecutive K blocks of the pre-tiled operand are contiguous: one bulk copy per slot
+          const __nv_bfloat16* src = (G.tm_a == 0 ? cx.A1 : G.tm_a == 1 ? cx.A2 : cx.Hm) + static_cast<size_t>(kb) * cx.RgP * 64;
+          bulk_load_1d(dst, src, n * a_bytes, &sm.a_full[rg.a_slot]);
+        } else {   // row-major x-embedder operand: box = 64 K x RgP rows starting at the group's first row (rows past R are zero-filled)
+          for (int j = 0; j < n; ++j) tma_load_2d(&p.tmaps[G.tm_a], &sm.a_full[rg.a_slot], dst + j * a_bytes, (kb + j) * 64, cx.row0, kEvictLast);
+        }
+      }
+      if (++rg.a_slot == WIN2_NA) { rg.a_slot = 0; rg.a_phase ^= 1; }
+    }
+    __syncwarp();
+  } else if (mw == 1) {
+    // ===================== MMA issuer: D[128 x nf] += A[128 x 16] . W[nf x 16]^T =====================
+    // The loop is warp-uniform (every lane waits, one elected lane issues) and keeps its per-K-block instruction count low: a
+    // single warp runs it at ~5 cycles per dependent instruction, and at 4 small MMAs per K block that, not the tensor pipe,
+    // sets the pace (measured 0.45 us per K block with ~150 instructions in the body).
+    const uint32_t idesc = make_idesc_bf16_f32(128, static_cast<uint32_t>(G.nf));
+    const int tile = G.nf * 128, kps = WIN2_W_BYTES / tile;              // K blocks per weight slot (same chunking as the producer)
+    const int kpa = WIN2_A_BYTES / a_bytes;                              // K blocks per activation slot
+    const uint64_t desc_hi = make_sw128_kmajor_desc(0);
+    const uint32_t w_base = smem_u32(sm.wring) >> 4, a_base = smem_u32(sm.aring) >> 4;
+    const uint32_t tile16 = tile >> 4, ab16 = a_bytes >> 4;
+    const bool leader = elect_one();
+    int w_slot = rg.w_slot, a_slot = rg.a_slot;
+    uint32_t w_phase = rg.w_phase, a_phase = rg.a_phase;
+    int j = 0, ja = 0;
+    uint32_t wa = w_base + w_slot * (WIN2_W_BYTES >> 4), aa = a_base + a_slot * (WIN2_A_BYTES >> 4);
+    uint32_t accum = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      const bool last = kb == kb1 - 1;
+      if (j == 0) mbar_wait_b(&sm.w_full[w_slot], w_phase, p.err_flag, 2);
+      if (ja == 0) mbar_wait_b(&sm.a_full[a_slot], a_phase, p.err_flag, 3);
+      tc_fence_after();
+      const bool w_done = (++j == kps) || last, a_done = (++ja == kpa) || last;
+      if (leader) {
+        if (kb == kb0) win_mark(p, epoch, 0);                            // first operands landed
+        const uint64_t dw = desc_hi | wa, da = desc_hi | aa;
+        umma_bf16(tmem_base, da, dw, idesc, accum);
+        umma_bf16(tmem_base, da + 2, dw + 2, idesc, 1u);
+        umma_bf16(tmem_base, da + 4, dw + 4, idesc, 1u);
+        umma_bf16(tmem_base, da + 6, dw + 6, idesc, 1u);
+        if (w_done) umma_commit(&sm.w_empty[w_slot]);
+        if (a_done) umma_commit(&sm.a_empty[a_slot]);
+        if (last) { umma_commit(sm.t_full); atomicAdd_block(sm.gate, 1); win_mark(p, epoch, 1); }   // quiet point: this stage's operands have landed
+      }
+      accum = 1u;
+      wa += tile16; aa += ab16;
+      if (w_done) { j = 0; if (++w_slot == WIN2_NW) { w_slot = 0; w_phase ^= 1; } wa = w_base + w_slot * (WIN2_W_BYTES >> 4); }
+      if (a_done) { ja = 0; if (++a_slot == WIN2_NA) { a_slot = 0; a_phase ^= 1; } aa = a_base + a_slot * (WIN2_A_BYTES >> 4); }
+    }
+    rg.w_slot = w_slot; rg.w_phase = w_phase; rg.a_slot = a_slot; rg.a_phase = a_phase;
+    __syncwarp();
+  } else if (mw >= 4) {
+    // ===================== epilogue: lane = token row, columns = this item's features =====================
+    const int quarter = warp & 3;
+    if (lane == 0) mbar_wait_b(sm.t_full, rg.t_phase, p.err_flag, 4);      // one poller per warp
+    __syncwarp();
+    rg.t_phase ^= 1;
+    tc_fence_after();
+    if (quarter == 0 && lane == 0) win_mark(p, epoch, 2);
+    if (quarter * 32 < cx.RgP) {
+      const int lr = quarter * 32 + lane;
+      const bool valid = lr < cx.nrows;
+      const int f0 = nt * G.nf;
+      float* acc = (G.out == 0 ? p.Pacc : G.out == 1 ? p.QKVacc : G.out == 2 ? p.Hacc : p.Vacc) + static_cast<size_t>(cx.row0 + lr) * G.N + f0;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+      const int ncol = min(G.nf, G.N - f0);                              // valid columns (multiple of 16)
+#pragma unroll 1
+      for (int c = 0; c < ncol; c += 16) {
+        float v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+        if (!valid) continue;
+        if (G.epi == 1) {
+          // fc1: Hm = bf16(GELU(acc + b)), written as 16-byte chunks of the pre-tiled operand (FMT.py:159-162)
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + f0 + c + j)), b1 = __ldg(reinterpret_cast<const float4*>(bias + f0 + c + j + 4));
+            uint4 t;
+            t.x = pack_bf16x2(gelu_tanh_fast(v[j] + b0.x), gelu_tanh_fast(v[j + 1] + b0.y));
+            t.y = pack_bf16x2(gelu_tanh_fast(v[j + 2] + b0.z), gelu_tanh_fast(v[j + 3] + b0.w));
+            t.z = pack_bf16x2(gelu_tanh_fast(v[j + 4] + b1.x), gelu_tanh_fast(v[j + 5] + b1.y));
+            t.w = pack_bf16x2(gelu_tanh_fast(v[j + 6] + b1.z), gelu_tanh_fast(v[j + 7] + b1.w));
+            *reinterpret_cast<uint4*>(cx.Hm + win_tiled_off(lr, f0 + c + j, cx.RgP)) = t;
+          }
+        } else if (G.pk == 1) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 8)
+            st_global_v8(acc + c + j, __float_as_uint(v[j]), __float_as_uint(v[j + 1]), __float_as_uint(v[j + 2]), __float_as_uint(v[j + 3]),
+                         __float_as_uint(v[j + 4]), __float_as_uint(v[j + 5]), __float_as_uint(v[j + 6]), __float_as_uint(v[j + 7]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) red_add_v4(acc + c + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+      if (quarter == 0 && lane == 0) win_mark(p, epoch, 3);
+    }
+    tc_fence_before();
+  }
+}
+
+// weight producer of the grouped schedule (warp 0): the same free-running ring, items from win_item2
+__device__ __forceinline__ void win_weight_producer2(const WinParams& p, const WinItems& items, const WinSmem& sm, int n_eval) {
+  int slot = 0; uint32_t phase = 0;
+  const int bs = p.fuse_gelu ? 7 : 8;
+  const int spe = 4 + bs * p.depth;                    // stages per evaluation
+  for (int e = 0; e < n_eval; ++e) {
+    for (int g = 0; g < p.n_gemms; ++g) {
+      const WinGemm& G = p.gemms[g];
+      const int4 item = items.it[g];
+      if (item.x < 0) continue;
+      const int nt = item.x, kb0 = item.y, kb1 = item.z;
+      // stage index of GEMM g inside an evaluation: 0 | 2 + bs * blk + {0 qkv, 2 proj, 4 fc1, 6 (5 when GELU is fused) fc2} | spe - 2
+      const int q = (g - 1) % 4;
+      const int si = g == 0 ? 0 : (g == p.n_gemms - 1 ? spe - 2 : 2 + bs * ((g - 1) / 4) + (q == 3 && p.fuse_gelu ? 5 : 2 * q));
+      const int need = e * spe + si - p.w_lookahead + 1;
+      if (need > 0) {
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile int*>(sm.gate) < need) {
+          __nanosleep(64);
+          if (clock64() - t0 > WIN_SPIN_LIMIT) win_fail(p.err_flag, 6);
+        }
+      }
+      const int tile = G.nf * 128, kps = WIN2_W_BYTES / tile;            // K blocks per ring slot
+      for (int kb = kb0; kb < kb1; kb += kps) {
+        const int n = min(kps, kb1 - kb);
+        mbar_wait_b(&sm.w_empty[slot], phase ^ 1, p.err_flag, 5);
+        mbar_expect_tx(&sm.w_full[slot], n * tile);
+        for (int j = 0; j < n; ++j)
+          tma_load_2d(&p.tmaps[G.tm_w], &sm.w_full[slot], sm.wring + slot * WIN2_W_BYTES + j * tile, (kb + j) * 64, nt * G.nf, kEvictNormal);
+        if (++slot == WIN2_NW) { slot = 0; phase ^= 1; }
+      }
+    }
   }
 }
 
@@ -269,14 +484,15 @@ __device__ __forceinline__ void win_gemm_stage(const WinParams& p, const WinGemm
 // Gating: the refill of the ring competes with the latency-critical loads of the stage in flight (measured: a SIMT stage's
 // L2 loads take 1.5 us instead of 0.65 us while 148 producers burst), so the weights of global stage s may only be
 // requested once `gate` (quiet points passed = stages whose own loads have landed) has reached s - w_lookahead + 1.
-__device__ __noinline__ void win_weight_producer(const WinParams& p, const WinSmem& sm, int n_eval) {
+__device__ __forceinline__ void win_weight_producer(const WinParams& p, const WinItems& items, const WinSmem& sm, int n_eval) {
   int slot = 0; uint32_t phase = 0;
   const int spe = 4 + 8 * p.depth;                     // stages per evaluation
   for (int e = 0; e < n_eval; ++e) {
     for (int g = 0; g < p.n_gemms; ++g) {
       const WinGemm& G = p.gemms[g];
-      int ft, kb0, kb1;
-      if (!win_item(G, ft, kb0, kb1)) continue;
+      const int4 item = items.it[g];
+      if (item.x < 0) continue;
+      const int ft = item.x, kb0 = item.y, kb1 = item.z;
       const int si = g == 0 ? 0 : (g == p.n_gemms - 1 ? spe - 2 : 2 + 8 * ((g - 1) / 4) + 2 * ((g - 1) % 4));
       const int need = e * spe + si - p.w_lookahead + 1;
       if (need > 0) {
@@ -319,7 +535,7 @@ __device__ __forceinline__ uint2 ld_nc_u2(const __nv_bfloat16* p) { return __ldg
 // then A1 = bf16( LayerNorm(X) * (1 + scale) + shift )  with this evaluation's table row  (FMT.py:168-169,174-175,197)
 // and the accumulator row (plus, after proj, the QKV accumulator row) is zeroed for its next use.
 template <int NV>
-__device__ __noinline__ void win_row_stage(const WinParams& p, float* red_smem, const __nv_bfloat16* __restrict__ table_e, int mode,
+__device__ __forceinline__ void win_row_stage(const WinParams& p, const WinCtx& cx, float* red_smem, const __nv_bfloat16* __restrict__ table_e, int mode,
                                               const float* __restrict__ bias, long long gate_off, long long shift_off, long long scale_off,
                                               bool zero_qkv) {
   constexpr int WPR = NV >= 4 ? 4 : NV;          // warps per row
@@ -329,7 +545,7 @@ __device__ __noinline__ void win_row_stage(const WinParams& p, float* red_smem, 
   const int grp = mw / WPR, wq = mw % WPR;
   const int H = p.s.H;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = blockIdx.x + gridDim.x * grp; r < p.R; r += gridDim.x * GROUPS) {
+  for (int r = cx.row0 + cx.rank + cx.nranks * grp; r < cx.row0 + cx.nrows; r += cx.nranks * GROUPS) {
     const int c0 = wq * (FPL * 128) + lane * 4;                       // first column of this lane; + i*128 per float4
     float* acc = p.Pacc + static_cast<size_t>(r) * H + c0;
     float* xr = p.X + static_cast<size_t>(r) * H + c0;
@@ -406,7 +622,7 @@ __device__ __noinline__ void win_row_stage(const WinParams& p, float* red_smem, 
       float v[4] = {(x[i].x - mean) * rstd, (x[i].y - mean) * rstd, (x[i].z - mean) * rstd, (x[i].w - mean) * rstd};
 #pragma unroll
       for (int k = 0; k < 4; ++k) v[k] = fmaf(v[k], 1.f + sc[k], sh[k]);
-      *reinterpret_cast<uint2*>(p.A1 + win_tiled_off(r, c0 + i * 128, p.Rp)) = f32x4_to_bf16(v);
+      *reinterpret_cast<uint2*>(cx.A1 + win_tiled_off(r - cx.row0, c0 + i * 128, cx.RgP)) = f32x4_to_bf16(v);
     }
     if (WPR > 1) named_bar_sync(3 + grp, WPR * 32);   // red_smem is reused by the next row of this group
   }
@@ -422,16 +638,20 @@ template <> struct F32Vec<4> { static __device__ __forceinline__ void ld(const f
 
 // Fast path (band of at most 5 keys = attention_window <= 2): U units per warp, all loads first, plain (not online) softmax.
 template <int VPL, int U /* units interleaved per warp */>
-__device__ __noinline__ void win_attn_band5(const WinParams& p, const float* __restrict__ bqkv) {
+__device__ __forceinline__ void win_attn_band5(const WinParams& p, const WinCtx& cx, const float* __restrict__ bqkv) {
   const int lane = threadIdx.x & 31, mw = (threadIdx.x >> 5) - 1;
   constexpr int hd = VPL * 32, KB = 5;
   const int N = p.s.N, heads = p.heads, H = p.s.H, ld = 3 * H;
-  const int n_units = p.R * heads;
+  const int n_units = cx.nrows * heads;
   const float scale = rsqrtf(static_cast<float>(hd));
   const int win = p.window;
-  const int stride = gridDim.x * 8;
+  const int stride = cx.nranks * 8;
+  // index arithmetic without runtime divisions on the critical path (a single warp pays ~150 cycles for each)
+  const bool h_pow2 = (heads & (heads - 1)) == 0;
+  const int h_shift = __ffs(heads) - 1;
+  const int sq0 = cx.row0 / N, fi0 = cx.row0 - sq0 * N;      // once per stage
 #pragma unroll 1
-  for (int u0 = blockIdx.x + gridDim.x * mw; u0 < n_units; u0 += U * stride) {
+  for (int u0 = cx.rank + cx.nranks * mw; u0 < n_units; u0 += U * stride) {
     int row[U], hh[U], j0[U], nk[U];
     bool valid[U];
     float q[U][VPL], kv[U][KB][VPL], vv[U][KB][VPL];
@@ -440,8 +660,11 @@ __device__ __noinline__ void win_attn_band5(const WinParams& p, const float* __r
       const int u = u0 + t * stride;
       valid[t] = u < n_units;
       const int uu = valid[t] ? u : u0;
-      hh[t] = uu % heads; row[t] = uu / heads;
-      const int fi = row[t] % N, sq = row[t] / N;
+      const int lr = h_pow2 ? (uu >> h_shift) : uu / heads;
+      hh[t] = h_pow2 ? (uu & (heads - 1)) : uu - lr * heads;
+      row[t] = cx.row0 + lr;
+      int fi = fi0 + lr, sq = sq0;
+      while (fi >= N) { fi -= N; ++sq; }
       const float* base = p.QKVacc + static_cast<size_t>(sq) * N * ld + hh[t] * hd + lane * VPL;
       j0[t] = max(0, fi - win);
       const int j1 = min(N - 1, fi + win);
@@ -486,7 +709,7 @@ __device__ __noinline__ void win_attn_band5(const WinParams& p, const float* __r
       }
       if (valid[t]) {
         const float inv = __fdividef(1.f, den);
-        __nv_bfloat16* op = p.A2 + win_tiled_off(row[t], hh[t] * hd + lane * VPL, p.Rp);   // VPL <= 4 elements stay inside one 16-byte chunk
+        __nv_bfloat16* op = cx.A2 + win_tiled_off(row[t] - cx.row0, hh[t] * hd + lane * VPL, cx.RgP);   // VPL <= 4 elements stay inside one 16-byte chunk
         float o[VPL];
 #pragma unroll
         for (int k = 0; k < VPL; ++k) o[k] = fmaf(acc[k], inv, __ldg(bq + 2 * H + k));   // sum_c p_c (v_c + b) / den = sum_c p_c v_c / den + b
@@ -503,16 +726,16 @@ __device__ __noinline__ void win_attn_band5(const WinParams& p, const float* __r
 
 // General band width: one unit per warp, keys in batches of 4 with an online softmax (compact code; rarely used).
 template <int VPL>
-__device__ __noinline__ void win_attn_wide(const WinParams& p, const float* __restrict__ bqkv) {
+__device__ __forceinline__ void win_attn_wide(const WinParams& p, const WinCtx& cx, const float* __restrict__ bqkv) {
   const int lane = threadIdx.x & 31, mw = (threadIdx.x >> 5) - 1;
   constexpr int hd = VPL * 32, KB = 4;
   const int N = p.s.N, heads = p.heads, H = p.s.H, ld = 3 * H;
-  const int n_units = p.R * heads;
+  const int n_units = cx.nrows * heads;
   const float scale = rsqrtf(static_cast<float>(hd));
   const int win = p.window;
 #pragma unroll 1
-  for (int u = blockIdx.x + gridDim.x * mw; u < n_units; u += gridDim.x * 8) {
-    const int h = u % heads, row = u / heads, fi = row % N, sq = row / N;
+  for (int u = cx.rank + cx.nranks * mw; u < n_units; u += cx.nranks * 8) {
+    const int h = u % heads, row = cx.row0 + u / heads, fi = row % N, sq = row / N;
     const float* base = p.QKVacc + static_cast<size_t>(sq) * N * ld + h * hd + lane * VPL;
     const float* bq = bqkv + h * hd + lane * VPL;
     float q[VPL], bk[VPL];
@@ -557,7 +780,7 @@ __device__ __noinline__ void win_attn_wide(const WinParams& p, const float* __re
       }
     }
     const float inv = __fdividef(1.f, den);
-    __nv_bfloat16* op = p.A2 + win_tiled_off(row, h * hd + lane * VPL, p.Rp);
+    __nv_bfloat16* op = cx.A2 + win_tiled_off(row - cx.row0, h * hd + lane * VPL, cx.RgP);
 #pragma unroll
     for (int k = 0; k < VPL; ++k) op[k] = __float2bfloat16_rn(fmaf(acc[k], inv, __ldg(bq + 2 * H + k)));
   }
@@ -571,19 +794,20 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
   return 0.5f * x * (1.0f + t);
 }
-__device__ __noinline__ void win_gelu_stage(const WinParams& p, const float* __restrict__ b1, unsigned epoch) {
+__device__ __forceinline__ void win_gelu_stage(const WinParams& p, const WinCtx& cx, const float* __restrict__ b1, unsigned epoch) {
   const int M4 = p.mlp_hidden;
-  const unsigned total4 = static_cast<unsigned>(p.R) * M4 / 4;
-  const unsigned stride = gridDim.x * WIN_MAIN;
+  const unsigned total4 = static_cast<unsigned>(cx.nrows) * M4 / 4;      // this group's elements; i = local float4 index
+  const unsigned stride = cx.nranks * WIN_MAIN;
+  float* hacc = p.Hacc + static_cast<size_t>(cx.row0) * M4;
   constexpr int NB = 6;                                  // float4 per thread per batch (R = 180, 4096 hidden: 5 per thread)
-  for (unsigned i0 = blockIdx.x * WIN_MAIN + (threadIdx.x - 32); i0 < total4; i0 += NB * stride) {
+  for (unsigned i0 = cx.rank * WIN_MAIN + (threadIdx.x - 32); i0 < total4; i0 += NB * stride) {
     float4 a[NB], b[NB];
     win_mark(p, epoch, 0);
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
       const unsigned i = i0 + k * stride;
       if (i < total4) {
-        a[k] = ldcg4(p.Hacc + static_cast<size_t>(i) * 4);
+        a[k] = ldcg4(hacc + static_cast<size_t>(i) * 4);
         b[k] = __ldg(reinterpret_cast<const float4*>(b1 + (i * 4) % static_cast<unsigned>(M4)));
       }
     }
@@ -595,9 +819,9 @@ __device__ __noinline__ void win_gelu_stage(const WinParams& p, const float* __r
         float v[4] = {gelu_tanh_fast(a[k].x + b[k].x), gelu_tanh_fast(a[k].y + b[k].y), gelu_tanh_fast(a[k].z + b[k].z), gelu_tanh_fast(a[k].w + b[k].w)};
         {
           const unsigned e4 = i * 4, M4u = static_cast<unsigned>(M4);
-          *reinterpret_cast<uint2*>(p.Hm + win_tiled_off(static_cast<int>(e4 / M4u), static_cast<int>(e4 % M4u), p.Rp)) = f32x4_to_bf16(v);
+          *reinterpret_cast<uint2*>(cx.Hm + win_tiled_off(static_cast<int>(e4 / M4u), static_cast<int>(e4 % M4u), cx.RgP)) = f32x4_to_bf16(v);
         }
-        *reinterpret_cast<float4*>(p.Hacc + static_cast<size_t>(i) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(hacc + static_cast<size_t>(i) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     win_mark(p, epoch, 2);
@@ -607,12 +831,12 @@ __device__ __noinline__ void win_gelu_stage(const WinParams& p, const float* __r
 
 // COMB stage: decoder bias, CFG combine (FMT.py:375-379,396-399), then the explicit Runge-Kutta bookkeeping of stage g of
 // step `step` (Euler: y += dt * v).  Writes the x-embedder operand `ax` of the next evaluation and zeroes Vacc.
-__device__ __noinline__ void win_comb_stage(const WinParams& p, int step, int g) {
+__device__ __forceinline__ void win_comb_stage(const WinParams& p, const WinCtx& cx, int step, int g) {
   const ModelShape& s = p.s;
   const int G = p.n_stages;
   const size_t per_branch = static_cast<size_t>(s.B) * s.N * s.W;
   const size_t nx = static_cast<size_t>(s.B) * s.L * s.W;
-  for (unsigned i = blockIdx.x * WIN_MAIN + (threadIdx.x - 32); i < per_branch; i += gridDim.x * WIN_MAIN) {   // R <= 256 rows: 32-bit indices
+  for (unsigned i = cx.all_rank * WIN_MAIN + (threadIdx.x - 32); i < per_branch; i += cx.all_n * WIN_MAIN) {   // R <= 256 rows: 32-bit indices
     const int j = static_cast<int>(i % static_cast<unsigned>(s.W));
     const int f = static_cast<int>((i / static_cast<unsigned>(s.W)) % static_cast<unsigned>(s.N)), b = static_cast<int>(i / static_cast<unsigned>(s.W * s.N));
     const bool cur = f >= s.P;
@@ -661,25 +885,28 @@ __device__ __noinline__ void win_comb_stage(const WinParams& p, int step, int g)
   }
 }
 
-__device__ __forceinline__ void win_attn_dispatch(const WinParams& p, const float* bqkv) {
+__device__ __forceinline__ void win_attn_dispatch(const WinParams& p, const WinCtx& cx, const float* bqkv) {
   const int hd = p.s.H / p.heads;
   if (p.window <= 2) {
-    if (hd == 128) win_attn_band5<4, 2>(p, bqkv);
-    else if (hd == 64) win_attn_band5<2, 2>(p, bqkv);
-    else win_attn_band5<1, 2>(p, bqkv);
+    if (hd == 128) win_attn_band5<4, 2>(p, cx, bqkv);
+    else if (hd == 64) win_attn_band5<2, 2>(p, cx, bqkv);
+    else win_attn_band5<1, 2>(p, cx, bqkv);
   } else {
-    if (hd == 128) win_attn_wide<4>(p, bqkv);
-    else if (hd == 64) win_attn_wide<2>(p, bqkv);
-    else win_attn_wide<1>(p, bqkv);
+    if (hd == 128) win_attn_wide<4>(p, cx, bqkv);
+    else if (hd == 64) win_attn_wide<2>(p, cx, bqkv);
+    else win_attn_wide<1>(p, cx, bqkv);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------- kernel
-template <int NV /* dim_h / 128 */>
+template <int NV /* dim_h / 128 */, bool GROUPED /* false: split-K over the whole grid; true: one group of CTAs per <= 128 rows */>
 __global__ void __launch_bounds__(WIN_THREADS, 1) fmt_window_kernel(const WinParams* __restrict__ pp) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ WinParams p;
   __shared__ float red_smem[16];
+  __shared__ WinItems items;
+  __shared__ WinRing rings[WIN_THREADS / 32];   // ring positions of each role warp live here between GEMM stages (registers are scarce: 168 at 288 threads)
+  __shared__ WinCtx cx;                  // shared, not local: a stack object is re-fetched from L2 after every grid barrier (the acquire invalidates L1)
   {
     const int4* src = reinterpret_cast<const int4*>(pp);
     int4* dst = reinterpret_cast<int4*>(&p);
@@ -687,23 +914,46 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) fmt_window_kernel(const WinPar
   }
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   WinSmem sm;
+  sm.nw = GROUPED ? WIN2_NW : WIN_NW;
+  sm.w_bytes = GROUPED ? WIN2_W_BYTES : WIN_W_BYTES;
   sm.wring = smem;
-  sm.aring = smem + WIN_NW * WIN_W_BYTES;
-  sm.stg = reinterpret_cast<float*>(sm.aring + WIN_A_RING);
-  sm.w_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm.stg) + 2 * WIN_STG_BYTES);
-  sm.w_empty = sm.w_full + WIN_NW;
-  sm.a_full = sm.w_empty + WIN_NW;
+  sm.aring = smem + sm.nw * sm.w_bytes;
+  sm.stg = reinterpret_cast<float*>(sm.aring + (GROUPED ? WIN2_A_RING : WIN_A_RING));     // staging exists in the split-K schedule only
+  sm.w_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm.stg) + (GROUPED ? 0 : 2 * WIN_STG_BYTES));
+  sm.w_empty = sm.w_full + WIN_MAX_NA;
+  sm.a_full = sm.w_empty + WIN_MAX_NA;
   sm.a_empty = sm.a_full + WIN_MAX_NA;
   sm.t_full = sm.a_empty + WIN_MAX_NA;
   sm.tmem_slot = reinterpret_cast<uint32_t*>(sm.t_full + 1);
   sm.gate = reinterpret_cast<int*>(sm.tmem_slot + 1);
   __syncthreads();
+  if (GROUPED && static_cast<int>(blockIdx.x) >= p.G * p.Cg) return;    // CTAs left over by 148 = G * Cg + rest have no work
+
+  if (threadIdx.x == 0) {
+    if (GROUPED) {
+      const int g = blockIdx.x / p.Cg;
+      const size_t t_a1 = static_cast<size_t>((p.s.H + 63) / 64) * p.RgP * 64, t_hm = static_cast<size_t>((p.mlp_hidden + 63) / 64) * p.RgP * 64;
+      cx.row0 = g * p.Rg; cx.nrows = p.Rg; cx.rank = blockIdx.x % p.Cg; cx.nranks = p.Cg;
+      cx.all_rank = blockIdx.x; cx.all_n = p.G * p.Cg; cx.RgP = p.RgP;
+      cx.A1 = p.A1 + g * t_a1; cx.A2 = p.A2 + g * t_a1; cx.Hm = p.Hm + g * t_hm;
+      cx.bar = p.bar_counter + 32 * (1 + g);
+    } else {
+      cx.row0 = 0; cx.nrows = p.R; cx.rank = blockIdx.x; cx.nranks = gridDim.x; cx.all_rank = blockIdx.x; cx.all_n = gridDim.x; cx.RgP = p.Rp;
+      cx.A1 = p.A1; cx.A2 = p.A2; cx.Hm = p.Hm; cx.bar = p.bar_counter;
+    }
+  }
+  __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int NA = WIN_A_RING / (p.Rp * 128);
+  for (int g = threadIdx.x; g < p.n_gemms; g += WIN_THREADS) {
+    int nt, kb0, kb1;
+    const bool has = GROUPED ? win_item2(p.gemms[g], cx, nt, kb0, kb1) : win_item(p.gemms[g], nt, kb0, kb1);
+    items.it[g] = make_int4(has ? nt : -1, kb0, kb1, 0);
+  }
+  int NA = GROUPED ? WIN2_NA : WIN_A_RING / (cx.RgP * 128);
   if (NA > WIN_MAX_NA) NA = WIN_MAX_NA;
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < WIN_NW; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
+    for (int i = 0; i < sm.nw; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
     for (int i = 0; i < WIN_MAX_NA; ++i) { mbar_init(&sm.a_full[i], 1); mbar_init(&sm.a_empty[i], 1); }
     mbar_init(sm.t_full, 1);
     *sm.gate = 0;
@@ -720,37 +970,51 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) fmt_window_kernel(const WinPar
   const int n_eval = p.n_steps * p.n_stages;
 
   if (warp == 0) {
-    if (lane == 0) win_weight_producer(p, sm, n_eval);
+    if (lane == 0) {
+      if (GROUPED) win_weight_producer2(p, items, sm, n_eval);
+      else win_weight_producer(p, items, sm, n_eval);
+    }
     __syncwarp();
   } else {
     // One call site per stage kind: the stage list of an evaluation is decoded from its index, so the GEMM stage (ring
-    // state in registers) is inlined exactly once and the hot code stays small.
-    //   0: x_embedder GEMM   1: ROW (init)   2 + 8*blk + {0: qkv GEMM, 1: ATTN, 2: proj GEMM, 3: ROW, 4: fc1 GEMM, 5: GELU,
+    // state in registers) is inlined exactly once and the hot code stays small.  With bs = 8 stages per block:
+    //   0: x_embedder GEMM   1: ROW (init)   2 + bs*blk + {0: qkv GEMM, 1: ATTN, 2: proj GEMM, 3: ROW, 4: fc1 GEMM, 5: GELU,
     //   6: fc2 GEMM, 7: ROW}   spe-2: decoder GEMM   spe-1: COMB
-    WinRing rg;
-    unsigned epoch = 0;
+    // (grouped schedule with the GELU fused into fc1's epilogue: bs = 7, {..., 4: fc1 GEMM + GELU, 5: fc2 GEMM, 6: ROW})
+    if (lane == 0) rings[warp] = WinRing();
+    __syncwarp();
+    unsigned epoch = 0, n_grp = 0, n_all = 0;          // barriers passed: total / of the group / of the whole grid
     const int D = p.depth;
-    const int spe = 4 + 8 * D;
+    const int bs = (GROUPED && p.fuse_gelu) ? 7 : 8;
+    const int spe = 4 + bs * D;
     const size_t eval_stride = static_cast<size_t>(p.R) * p.NT;
     const long long H = p.s.H;
     for (int e = 0; e < n_eval; ++e) {
       const __nv_bfloat16* table_e = p.table + static_cast<size_t>(e) * eval_stride;
+      int blk_ctr = 0, jj = 0;                             // block and position inside it of stage si (counted, not divided)
       for (int si = 0; si < spe; ++si) {
-        const int j = (si - 2) & 7, blk = (si - 2) >> 3;
         const bool is_edge = si < 2 || si >= spe - 2;
+        const int blk = blk_ctr;
+        int j = is_edge ? 0 : jj;                          // position inside the block in the 8-stage numbering
+        if (!is_edge && ++jj == bs) { jj = 0; ++blk_ctr; }
+        if (bs == 7 && j >= 5) ++j;
         const bool is_gemm = is_edge ? (si == 0 || si == spe - 2) : ((j & 1) == 0);
         if (is_gemm) {
           const int g = si == 0 ? 0 : (si == spe - 2 ? 1 + 4 * D : 1 + 4 * blk + (j >> 1));
-          win_gemm_stage(p, p.gemms[g], sm, rg, NA, tmem_base, epoch);
+          WinRing rg = rings[warp];
+          if (GROUPED) win_gemm2_stage(p, cx, p.gemms[g], items.it[g], sm, rg, tmem_base, epoch, (!is_edge && j == 4) ? p.b_fc1[blk] : nullptr);
+          else win_gemm_stage(p, p.gemms[g], items.it[g], sm, rg, NA, tmem_base, epoch);
+          if (lane == 0) rings[warp] = rg;
+          __syncwarp();
         } else {
           if (si == spe - 1) {
-            win_comb_stage(p, e / p.n_stages, e % p.n_stages);
+            win_comb_stage(p, cx, e / p.n_stages, e % p.n_stages);
           } else if (si == 1) {
-            win_row_stage<NV>(p, red_smem, table_e, 0, p.b_x, 0, 0, H, false);      // LN + modulate with block 0's (shift_msa, scale_msa)
+            win_row_stage<NV>(p, cx, red_smem, table_e, 0, p.b_x, 0, 0, H, false);      // LN + modulate with block 0's (shift_msa, scale_msa)
           } else if (j == 1) {
-            win_attn_dispatch(p, p.b_qkv[blk]);
+            win_attn_dispatch(p, cx, p.b_qkv[blk]);
           } else if (j == 5) {
-            win_gelu_stage(p, p.b_fc1[blk], epoch);
+            win_gelu_stage(p, cx, p.b_fc1[blk], epoch);
           } else {
             const long long base = static_cast<long long>(blk) * 6 * H;
             // j == 3: after proj -> gate_msa, then the mlp modulation; j == 7: after fc2 -> gate_mlp, then the NEXT block's msa
@@ -758,11 +1022,14 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) fmt_window_kernel(const WinPar
             const bool after_proj = (j == 3);
             const long long gate_off = base + (after_proj ? 2 : 5) * H;
             const long long mod = after_proj ? base + 3 * H : base + 6 * H;
-            win_row_stage<NV>(p, red_smem, table_e, 1, after_proj ? p.b_proj[blk] : p.b_fc2[blk], gate_off, mod, mod + H, after_proj);
+            win_row_stage<NV>(p, cx, red_smem, table_e, 1, after_proj ? p.b_proj[blk] : p.b_fc2[blk], gate_off, mod, mod + H, after_proj);
           }
           if (threadIdx.x == 32) atomicAdd(sm.gate, 1);                             // quiet point of a SIMT stage: its loads have landed
         }
-        win_grid_sync(p, epoch);
+        // The CFG combine reads every branch, and the next x-embedder GEMM reads what it wrote: the barriers around COMB span
+        // the whole grid; every other stage only depends on rows of its own group.
+        if (!GROUPED || si >= spe - 2) { ++n_all; win_grid_sync(p, epoch, p.bar_counter, n_all * cx.all_n); }
+        else { ++n_grp; win_grid_sync(p, epoch, cx.bar, n_grp * cx.nranks); }
       }
     }
   }

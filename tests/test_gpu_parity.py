@@ -205,17 +205,22 @@ def test_window_kernel_matches_per_op_path(pkg, monkeypatch, method, nfe, nb_sca
     g = torch.Generator().manual_seed(5)
     noise = torch.stack([torch.randn(B, d.frames_per_clip, d.dim_w, generator=g) for _ in range(3)]).to(DEV)
     outs = {}
-    for flag in ("1", "0"):
-        monkeypatch.setenv("FMT_WINDOW", flag)
+    # "2": grouped window kernel (one slice of the SMs per sequence, GELU fused into fc1's epilogue); "2s": same with the
+    # separate GELU stage and a 2-way K split of fc1; "1": split-K window kernel; "0": one kernel per op
+    for flag in ("2", "2s", "1", "0"):
+        monkeypatch.setenv("FMT_WINDOW", flag[0])
+        monkeypatch.setenv("FMT_WIN_FUSE_GELU", "0" if flag == "2s" else "1")
+        monkeypatch.setenv("FMT_WIN_PK", "0,0,2,0" if flag == "2s" else "0,0,0,0")
         be = pkg.FmtBackend(cases.weights("full"), pkg.Dims(), DEV)
         be.configure(B, pkg.n_branches_for(a, r, e, inc), False, nfe, method, "bf16")
-        assert be.window_kernel_status() == (0 if flag == "1" else -1)
+        assert be.window_kernel_status() == (0 if flag != "0" else -1)
         outs[flag] = be.sample_clip(r_s, wa, we, T, noise, a, r, e).cpu()
         torch.cuda.synchronize()
-        assert be.window_kernel_status() == (0 if flag == "1" else -1)
+        assert be.window_kernel_status() == (0 if flag != "0" else -1)
         be.close()
-    assert torch.isfinite(outs["1"]).all()
-    assert cases.max_abs(outs["1"], outs["0"]) <= 1e-2, cases.max_abs(outs["1"], outs["0"])
+    for flag in ("2", "2s", "1"):
+        assert torch.isfinite(outs[flag]).all(), flag
+        assert cases.max_abs(outs[flag], outs["0"]) <= 1e-2, (flag, cases.max_abs(outs[flag], outs["0"]))
 
 
 def test_large_batch_matches_oracle(pkg):

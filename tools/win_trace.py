@@ -28,11 +28,15 @@ buf = np.zeros(n, dtype=np.int64)
 be.lib.fmt_debug_window_trace(be._handle, buf.ctypes.data_as(C.c_void_p), n)
 n_cta = torch.cuda.get_device_properties(0).multi_processor_count
 full = buf.reshape(n_cta, -1, 6).astype(np.float64)
+full = full[full[:, :, 0].max(axis=1) > 0]      # CTAs without work (grouped schedule: 148 - G * Cg) leave no stamps
 tr = full[:, :, :2]
 marks = full[:, :, 2:]
 nbar = tr.shape[1]
 per_eval = nbar // (nfe - 1)
-names = ["x_emb G", "row0"] + sum([[f"b{b} qkv G", f"b{b} attn", f"b{b} proj G", f"b{b} row", f"b{b} fc1 G", f"b{b} gelu", f"b{b} fc2 G", f"b{b} row2"] for b in range(8)], []) + ["dec G", "comb"]
+if os.environ.get("FMT_WINDOW") == "2" and os.environ.get("FMT_WIN_FUSE_GELU", "1") != "0":
+    per_eval = 4 + 7 * 8          # grouped schedule with the GELU fused into fc1's epilogue (the trace buffer keeps the 68-stage stride)
+blk_names = ["qkv G", "attn", "proj G", "row", "fc1 G", "gelu", "fc2 G", "row2"] if per_eval == 4 + 8 * 8 else ["qkv G", "attn", "proj G", "row", "fc1 G", "fc2 G", "row2"]
+names = ["x_emb G", "row0"] + sum([[f"b{b} {n}" for n in blk_names] for b in range(8)], []) + ["dec G", "comb"]
 clk = 1.9  # GHz, approximate (SM clocks)
 work = tr[:, 1:, 0] - tr[:, :-1, 1]          # stage s work = arrive[s] - pass[s-1]   (per CTA)
 wait = tr[:, :, 1] - tr[:, :, 0]             # barrier wait
