@@ -459,7 +459,6 @@ static int setup_window(FmtHandle* h, cudaStream_t st) {
   wp.tmaps = static_cast<const CUtensorMap*>(h->win_tmaps.p);
   wp.w_lookahead = 1;
   if (const char* e = getenv("FMT_WIN_LA")) wp.w_lookahead = atoi(e);
-  if (const char* e = getenv("FMT_WIN_DBG")) wp.dbg = atoi(e);
   if (getenv("FMT_WIN_TRACE") && atoi(getenv("FMT_WIN_TRACE")) != 0) {
     h->win_trace_stride = h->n_eval * (4 + 8 * D);       // upper bound (the grouped schedule with the fused GELU has 4 + 7 * D stages)
     FMT_OK(dev_alloc(h, h->win_trace, static_cast<size_t>(grid) * h->win_trace_stride * 6 * sizeof(long long)));

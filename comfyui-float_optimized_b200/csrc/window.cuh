@@ -92,7 +92,6 @@ struct WinParams {
   // pre-tiled operand buffers of RgP (64 or 128) rows; bar_counter[32 * (1 + g)] is the group's barrier, bar_counter[0] the global one
   int G, Cg, Rg, RgP;
   int fuse_gelu;                       // 1: fc1's epilogue writes Hm, evaluation has 4 + 7 * depth stages
-  int dbg;                             // timing experiments only (FMT_WIN_DBG; results are wrong when set): 1 = no MMAs, 2 = no activation loads, 4 = no weight loads
 };
 
 // What a CTA works on in the SIMT stages: all rows / all CTAs in the split-K schedule, one group's rows / CTAs in the grouped one.
