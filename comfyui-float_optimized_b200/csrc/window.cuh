@@ -173,6 +173,8 @@ __device__ __forceinline__ void win_grid_sync(const WinParams& p, unsigned& epoc
     if (tr) tr[0] = clock64();
     red_release_gpu_add(counter, 1u);
     const long long t0 = clock64();
+    // acquire loads, back to back.  Measured alternative: relaxed polls (with 0-200 ns pauses) and one fence.acq_rel.gpu after the
+    // last one avoid the CCTL.IVALL per poll but cost 25 us per ODE step more - the full fence drains this SM's outstanding writes.
     while (ld_acquire_gpu(counter) < target) {
       if (clock64() - t0 > WIN_SPIN_LIMIT) win_fail(p.err_flag, 100 + static_cast<int>(epoch & 0xffff));
     }
