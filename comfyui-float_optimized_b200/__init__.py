@@ -1,5 +1,6 @@
 """B200-native FMT motion-latent sampler: drop-in ComfyUI nodes for the sampling path of ComfyUI-FLOAT_Optimized."""
 from .nodes import NODE_CLASS_MAPPINGS, NODE_DISPLAY_NAME_MAPPINGS, FloatSampleMotionSequenceRD_VA, FloatSampleMotionSequenceRD  # noqa: F401
+from .audio import AudioProjectionBackend, AudioProjectionLayer, FloatApplyAudioProjection, projection_backend_for  # noqa: F401
 from .options import BaseOptions, FmtModel, TORCHDIFFEQ_FIXED_STEP_SOLVERS  # noqa: F401
 from .sampler import (Dims, FmtBackend, FmtError, backend_for, perform_ode_sampling_loop, float_sample,  # noqa: F401
                       build_schedule, n_branches_for, draw_window_noise, SOLVERS)

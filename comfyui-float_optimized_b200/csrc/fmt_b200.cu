@@ -7,6 +7,7 @@
 #include "kernels.cuh"
 #include "window.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 #include <cstdarg>
@@ -668,6 +669,21 @@ static int make_linear(FmtHandle* h, Linear& L, const void* w, const void* b, in
   return 0;
 }
 
+static int debug_handle(FmtHandle& h) {
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return set_err(-4, "device is sm_%d%d; sm_100a required", prop.major, prop.minor);
+  h.device = dev; h.num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_OK(cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres));
+  REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+  h.encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  return 0;
+}
+
 extern "C" {
 
 int32_t fmt_abi_version(void) { return FMT_ABI_VERSION; }
@@ -1041,19 +1057,100 @@ int32_t fmt_velocity(FmtHandle* h, const FmtEval* ev, void* stream) {
 }
 
 // ------------------------------------------------------------------------------------------------ diagnostics
-static int debug_handle(FmtHandle& h) {
-  int dev = 0;
-  CUDA_OK(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  CUDA_OK(cudaGetDeviceProperties(&prop, dev));
-  if (prop.major != 10) return set_err(-4, "device is sm_%d%d; sm_100a required", prop.major, prop.minor);
-  h.device = dev; h.num_sms = prop.multiProcessorCount;
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  CUDA_OK(cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres));
-  REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
-  h.encode = reinterpret_cast<PFN_encodeTiled>(fn);
+
+// ------------------------------------------------------------------------------------------------ audio projection
+// wa = SiLU(LayerNorm(Linear(wav2vec features)))  -  FLOAT.py:338-342, applied by FloatApplyAudioProjection (nodes_vadv.py:147-198)
+struct FmtProj {
+  FmtHandle h;            // bare handle: device, SM count, tensor-map encoder, launch counters
+  Linear lin;
+  float *ln_w = nullptr, *ln_b = nullptr;
+  float eps = 1e-5f;
+  DevBuf x32, x16, y, o;
+};
+
+int32_t fmt_proj_create(int32_t in_dim, int32_t out_dim, const float* w, const float* b, const float* ln_w, const float* ln_b, float ln_eps,
+                        int32_t location, int32_t device, FmtProj** out) {
+  REQUIRE(w && b && ln_w && ln_b && out, "fmt_proj_create: null argument");
+  REQUIRE(in_dim > 0 && in_dim % 16 == 0 && out_dim > 0 && out_dim % 32 == 0, "fmt_proj_create: in_dim %% 16 and out_dim %% 32 required (got %d -> %d)",
+          in_dim, out_dim);
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return set_err(-4, "fmt_proj_create: no CUDA device - this library has no CPU fallback");
+  REQUIRE(device >= 0 && device < n_dev, "fmt_proj_create: device %d out of range (%d devices)", device, n_dev);
+  CUDA_OK(cudaSetDevice(device));
+  FmtProj* p = new FmtProj();
+  int rc = debug_handle(p->h);
+  if (rc == 0) rc = make_linear(&p->h, p->lin, w, b, out_dim, in_dim, in_dim, location);
+  if (rc == 0) rc = upload(&p->h, ln_w, out_dim, location, &p->ln_w);
+  if (rc == 0) rc = upload(&p->h, ln_b, out_dim, location, &p->ln_b);
+  if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) rc = set_err(-2, "fmt_proj_create: weight packing failed");
+  if (rc != 0) { for (void* q : p->h.owned) cudaFree(q); delete p; return rc; }
+  p->eps = ln_eps;
+  p->h.use_pdl = false;
+  *out = p;
   return 0;
+}
+
+int32_t fmt_proj_destroy(FmtProj* p) {
+  if (!p) return 0;
+  cudaSetDevice(p->h.device);
+  cudaDeviceSynchronize();
+  for (void* q : p->h.owned) cudaFree(q);
+  for (DevBuf* bf : {&p->x32, &p->x16, &p->y, &p->o})
+    if (bf->p) cudaFree(bf->p);
+  delete p;
+  return 0;
+}
+
+// x: (rows, in_dim) fp32, out: (rows, out_dim) fp32, both at `location`.  FMT_MODE_BF16: bf16 tcgen05 GEMM with fp32 accumulation,
+// LayerNorm / SiLU in fp32; FMT_MODE_FP32_VALIDATE: fp32 SIMT GEMM.
+int32_t fmt_proj_apply(FmtProj* p, const float* x, int64_t rows, float* out, int32_t mode, int32_t location, void* stream) {
+  REQUIRE(p && x && out, "fmt_proj_apply: null argument");
+  REQUIRE(rows > 0 && rows < (1ll << 31), "fmt_proj_apply: rows = %lld out of range", static_cast<long long>(rows));
+  REQUIRE(mode == FMT_MODE_BF16 || mode == FMT_MODE_FP32_VALIDATE, "fmt_proj_apply: unknown mode %d", mode);
+  FmtHandle* h = &p->h;
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int K = p->lin.K, N = p->lin.N, M = static_cast<int>(rows);
+  const size_t nx = static_cast<size_t>(rows) * K, ny = static_cast<size_t>(rows) * N;
+  const float* xd = x;
+  if (location == FMT_LOC_HOST) {
+    FMT_OK(dev_alloc(h, p->x32, nx * sizeof(float)));
+    CUDA_OK(cudaMemcpyAsync(p->x32.p, x, nx * sizeof(float), cudaMemcpyHostToDevice, st));
+    xd = static_cast<const float*>(p->x32.p);
+  }
+  FMT_OK(dev_alloc(h, p->y, ny * sizeof(float)));
+  EpiParams ep = epi(EPI_STORE, M, N, p->lin.b, p->y.p, N, 1);
+  if (mode == FMT_MODE_BF16) {
+    FMT_OK(dev_alloc(h, p->x16, nx * sizeof(bf16)));
+    const size_t n8 = nx / 8;                                   // K % 16 == 0
+    const unsigned blocks = static_cast<unsigned>(std::min<size_t>((n8 + 255) / 256, static_cast<size_t>(h->num_sms) * 16));
+    f32_to_bf16_kernel<<<blocks, 256, 0, st>>>(xd, static_cast<bf16*>(p->x16.p), n8);
+    LAUNCH_CHECK(); count_launch(h);
+    FMT_OK(gemm_bf16(h, static_cast<const bf16*>(p->x16.p), K, p->lin.w16, K, ep, K, st));
+  } else {
+    FMT_OK(gemm_f32(h, xd, K, p->lin.w32, K, ep, K, st));
+  }
+  float* od = out;
+  if (location == FMT_LOC_HOST) {
+    FMT_OK(dev_alloc(h, p->o, ny * sizeof(float)));
+    od = static_cast<float*>(p->o.p);
+  }
+  const int warps = 8;
+  ln_silu_kernel<<<static_cast<unsigned>((rows + warps - 1) / warps), warps * 32, 0, st>>>(static_cast<const float*>(p->y.p), rows, N, p->ln_w, p->ln_b, p->eps, od);
+  LAUNCH_CHECK(); count_launch(h);
+  if (location == FMT_LOC_HOST) {
+    CUDA_OK(cudaMemcpyAsync(out, od, ny * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+int64_t fmt_proj_launch_count(const FmtProj* p, int32_t reset) {
+  if (!p) return 0;
+  FmtProj* q = const_cast<FmtProj*>(p);
+  const long long n = q->h.launches;
+  if (reset) q->h.launches = 0;
+  return n;
 }
 
 int32_t fmt_debug_gemm_bf16(const void* A, const void* W, const float* bias, float* out, int32_t M, int32_t N, int32_t K, int32_t block_n, void* stream) {

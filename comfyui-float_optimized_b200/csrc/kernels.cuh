@@ -495,6 +495,53 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int rows, int 
   const size_t r = i / Kpad;
   dst[i] = __float2bfloat16_rn(k < K ? src[r * K + k] : 0.f);
 }
+// fp32 -> bf16 of a dense activation matrix, 8 elements per thread (two 16-byte loads, one 16-byte store): the HBM-bound pass in
+// front of the audio-projection GEMM (n % 8 == 0)
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n8) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(src) + 2 * i), b = __ldcs(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    uint4 t;
+    t.x = pack_bf16x2(a.x, a.y); t.y = pack_bf16x2(a.z, a.w); t.z = pack_bf16x2(b.x, b.y); t.w = pack_bf16x2(b.z, b.w);
+    reinterpret_cast<uint4*>(dst)[i] = t;
+  }
+}
+
+// Audio projection tail (FLOAT.py:338-342: Linear -> LayerNorm(affine, eps) -> SiLU): one warp per row of the GEMM output.
+__global__ void ln_silu_kernel(const float* __restrict__ y, long long rows, int N, const float* __restrict__ g, const float* __restrict__ b,
+                               float eps, float* __restrict__ out) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* yr = y + row * N;
+  float sum = 0.f;
+  for (int c = lane * 4; c < N; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(yr + c);
+    sum += (v.x + v.y) + (v.z + v.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / static_cast<float>(N);
+  float var = 0.f;
+  for (int c = lane * 4; c < N; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(yr + c);
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    var += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / static_cast<float>(N) + eps);
+  for (int c = lane * 4; c < N; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(yr + c);
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c)), bb = __ldg(reinterpret_cast<const float4*>(b + c));
+    float t[4] = {(v.x - mean) * rstd * gg.x + bb.x, (v.y - mean) * rstd * gg.y + bb.y, (v.z - mean) * rstd * gg.z + bb.z,
+                  (v.w - mean) * rstd * gg.w + bb.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[k] = t[k] / (1.f + expf(-t[k]));          // SiLU
+    *reinterpret_cast<float4*>(out + row * N + c) = make_float4(t[0], t[1], t[2], t[3]);
+  }
+}
+
 __global__ void pad_weight_f32_kernel(const float* __restrict__ src, int rows, int K, float* __restrict__ dst, int Kpad) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<size_t>(rows) * Kpad) return;

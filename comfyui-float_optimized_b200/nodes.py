@@ -192,6 +192,8 @@ class FloatSampleMotionSequenceRD:
         return (r_d.cpu(), float_pipe)
 
 
-NODE_CLASSES = [FloatSampleMotionSequenceRD_VA, FloatSampleMotionSequenceRD]
+from .audio import FloatApplyAudioProjection  # noqa: E402  (the node in front of the sampler)
+
+NODE_CLASSES = [FloatSampleMotionSequenceRD_VA, FloatSampleMotionSequenceRD, FloatApplyAudioProjection]
 NODE_CLASS_MAPPINGS = {c.UNIQUE_NAME: c for c in NODE_CLASSES}
 NODE_DISPLAY_NAME_MAPPINGS = {c.UNIQUE_NAME: c.DISPLAY_NAME for c in NODE_CLASSES}

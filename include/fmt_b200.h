@@ -165,6 +165,18 @@ FMT_API int32_t fmt_window_kernel_status(const FmtHandle* h);
  * [cta][barrier][arrive, pass] in SM clocks, into `out` (HOST); returns the element count (call with NULL to size). */
 FMT_API int64_t fmt_debug_window_trace(const FmtHandle* h, int64_t* out, int64_t max_elems);
 
+/* ---- audio projection in front of the sampler ----
+ * Replaces the nn.Sequential(Linear(in_dim, dim_w), LayerNorm(dim_w), SiLU) that FloatApplyAudioProjection runs
+ * (src/nodes/nodes_vadv.py:147-198; module built in src/nodes/models/float/FLOAT.py:338-342 and
+ * src/nodes/nodes_vadv_loader.py:228-257): wa = SiLU(LayerNorm(x W^T + b)).  in_dim = 9216 (12 stacked wav2vec layers) or 768. */
+typedef struct FmtProj FmtProj;
+FMT_API int32_t fmt_proj_create(int32_t in_dim, int32_t out_dim, const float* linear_w /* (out_dim, in_dim) */, const float* linear_b,
+                                const float* ln_w, const float* ln_b, float ln_eps, int32_t location, int32_t device, FmtProj** out);
+FMT_API int32_t fmt_proj_destroy(FmtProj* p);
+/* x (rows, in_dim) fp32 -> out (rows, out_dim) fp32, both at `location` (FMT_LOC_HOST synchronises the stream).  mode as in FmtPlan. */
+FMT_API int32_t fmt_proj_apply(FmtProj* p, const float* x, int64_t rows, float* out, int32_t mode, int32_t location, void* stream);
+FMT_API int64_t fmt_proj_launch_count(const FmtProj* p, int32_t reset);
+
 /* ---- diagnostic entry points (unit tests of the kernels; not used by the node) ---- */
 /* out[M,N] (fp32) = A[M,K] (bf16 bits) @ W[N,K]^T (bf16 bits) + bias[N], through the tcgen05/TMA GEMM. */
 FMT_API int32_t fmt_debug_gemm_bf16(const void* A, const void* W, const float* bias, float* out, int32_t M, int32_t N,

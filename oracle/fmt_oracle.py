@@ -299,3 +299,11 @@ def float_sample_legacy(W, d: FmtDims, r_s, wa, we, opt_nfe: int = 10, a_cfg_sca
         sample = odeint_fixed(f, x0, time, "euler")
         outs.append(sample)
     return torch.cat(outs, dim=1)[:, :T]
+
+
+def audio_projection(P, x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """``AudioEncoder.audio_projection`` (FLOAT.py:338-342) as applied by FloatApplyAudioProjection (nodes_vadv.py:188-192):
+    SiLU(LayerNorm(Linear(x))) over the last dimension; ``P`` holds the Sequential's state-dict keys."""
+    y = F.linear(x, P["0.weight"], P["0.bias"])
+    y = F.layer_norm(y, (y.shape[-1],), P["1.weight"], P["1.bias"], eps)
+    return F.silu(y)

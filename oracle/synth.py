@@ -125,3 +125,23 @@ def synth_inputs(d: FmtDims, batch: int, num_frames: int, seed: int = 7, dynamic
     else:
         we = torch.softmax(torch.randn(batch, 1, d.dim_e, generator=g), dim=-1)
     return r_s.contiguous(), wa.contiguous(), we.contiguous()
+
+
+def synth_projection(in_dim: int, dim_a: int = 512, seed: int = 0) -> dict:
+    """Seeded weights of the audio projection Sequential(Linear(in_dim, dim_a), LayerNorm(dim_a), SiLU)
+    (FLOAT.py:338-342, nodes_vadv_loader.py:233-240) under its state-dict keys; the LayerNorm affine is perturbed so that
+    it is exercised (the reference initialises it to weight 1, bias 0)."""
+    g = torch.Generator().manual_seed(3000 + seed)
+    bound = 1.0 / math.sqrt(in_dim)
+    return {
+        "0.weight": (torch.rand(dim_a, in_dim, generator=g) * 2 - 1) * bound,
+        "0.bias": (torch.rand(dim_a, generator=g) * 2 - 1) * bound,
+        "1.weight": 1.0 + 0.1 * torch.randn(dim_a, generator=g),
+        "1.bias": 0.05 * torch.randn(dim_a, generator=g),
+    }
+
+
+def synth_wav2vec_features(batch: int, num_frames: int, in_dim: int, seed: int = 7) -> torch.Tensor:
+    """Stand-in for the interpolated wav2vec2 hidden states (B, T, in_dim): unit-variance features with a per-layer offset."""
+    g = torch.Generator().manual_seed(4000 + seed)
+    return torch.randn(batch, num_frames, in_dim, generator=g) + 0.2 * torch.randn(1, 1, in_dim, generator=g)

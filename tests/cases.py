@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 from golden.make_golden import CASES, case_inputs, cfv_extra_inputs, dims_of  # noqa: F401  (same recipe code that made the fixtures)
-from oracle.synth import FmtDims, SMALL_DIMS, synth_state_dict
+from oracle.synth import FmtDims, SMALL_DIMS, synth_state_dict, synth_projection, synth_wav2vec_features
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -33,3 +33,11 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
 
 def max_abs(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a.double() - b.double()).abs().max())
+
+
+def projection_weights(rec) -> dict:
+    return synth_projection(rec["in_dim"], FmtDims().dim_a, seed=rec["seed"])
+
+
+def projection_input(rec) -> torch.Tensor:
+    return synth_wav2vec_features(rec["B"], rec["T"], rec["in_dim"], seed=rec["seed"])

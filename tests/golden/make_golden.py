@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
-from oracle.synth import FmtDims, SMALL_DIMS, synth_state_dict, synth_inputs  # noqa: E402
+from oracle.synth import FmtDims, SMALL_DIMS, synth_state_dict, synth_inputs, synth_projection, synth_wav2vec_features  # noqa: E402
 import refshim  # noqa: E402
 
 FULL = FmtDims()
@@ -54,6 +54,9 @@ CASES = {
     "small_static": dict(entry="va", dims="small", B=3, T=31, nfe=6, a=2.0, r=1.0, e=1.0, seed=50),
     "small_dynamic": dict(entry="va", dims="small", B=2, T=40, nfe=4, a=1.5, r=1.0, e=2.0, seed=51, dynamic_we=True),
     "small_rcfg": dict(entry="va", dims="small", B=2, T=24, nfe=5, a=2.0, r=2.0, e=1.0, seed=52, include_r_cfg=True),
+    # FloatApplyAudioProjection (nodes_vadv.py:147-198) on 12 stacked wav2vec layers / the last layer only
+    "proj_stacked": dict(entry="proj", dims="full", B=2, T=37, in_dim=9216, seed=60),
+    "proj_last": dict(entry="proj", dims="full", B=1, T=100, in_dim=768, seed=61),
 }
 
 
@@ -92,8 +95,23 @@ def ref_model(dims_name):
     return _models[dims_name]
 
 
+def projection_layer(rec):
+    """The module LoadAudioProjectionLayer builds (nodes_vadv_loader.py:233-257), with the seeded weights."""
+    layer = torch.nn.Sequential(torch.nn.Linear(rec["in_dim"], FULL.dim_a), torch.nn.LayerNorm(FULL.dim_a), torch.nn.SiLU())
+    layer.load_state_dict(synth_projection(rec["in_dim"], FULL.dim_a, seed=rec["seed"]))
+    layer.inferred_input_feature_dim = rec["in_dim"]
+    layer.target_device = torch.device("cpu")
+    return layer.eval()
+
+
 @torch.no_grad()
 def run_case(name, rec):
+    if rec["entry"] == "proj":
+        refshim.load_reference()
+        node = importlib.import_module("refnodes.nodes_vadv").FloatApplyAudioProjection()
+        x = synth_wav2vec_features(rec["B"], rec["T"], rec["in_dim"], seed=rec["seed"])
+        (out,) = node.apply_projection(x, projection_layer(rec))
+        return out.detach().cpu().float().numpy()
     ref, model, opt = ref_model(rec["dims"])
     d = dims_of(rec)
     r_s, wa, we = case_inputs(rec)

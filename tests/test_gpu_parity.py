@@ -73,6 +73,7 @@ def run_node(pkg, name, mode):
 
 
 CLIP_CASES = [n for n, r in cases.CASES.items() if r["entry"] in ("va", "adv", "legacy")]
+PROJ_CASES = [n for n, r in cases.CASES.items() if r["entry"] == "proj"]
 CFV_CASES = [n for n, r in cases.CASES.items() if r["entry"] == "cfv"]
 
 
@@ -293,3 +294,48 @@ def test_dynamic_emotion_sweeps(pkg, nfe, a, e):
                                                                        0.1, 0.1, 0.1, True, 8, _noise=noise)
     ref = _oracle_on_gpu(d, r_s, wa, we, T, noise, nfe=nfe, a_cfg_scale=a, r_cfg_scale=1.0, e_cfg_scale=e)
     assert cases.max_abs(out, ref) <= 2e-2, cases.max_abs(out, ref)
+
+
+# ---------------------------------------------------------------------------------------------- SURVEY.md §8f rank 2
+def _projection_layer(pkg, rec, device=DEV):
+    layer = pkg.AudioProjectionLayer(rec["in_dim"], 512, target_device=device)
+    layer.load_state_dict(cases.projection_weights(rec))
+    return layer
+
+
+@pytest.mark.parametrize("name", PROJ_CASES)
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_audio_projection_matches_reference(pkg, name, mode):
+    """FloatApplyAudioProjection (nodes_vadv.py:147-198) against the fixture the reference node produced: CPU tensor in,
+    CPU tensor out; fp32 validation mode 1e-4 relative, bf16 mode 2e-2 max-abs."""
+    rec = cases.CASES[name]
+    ref = cases.golden(name)
+    (out,) = pkg.FloatApplyAudioProjection().apply_projection(cases.projection_input(rec), _projection_layer(pkg, rec), _mode=mode)
+    assert out.device.type == "cpu" and out.dtype == torch.float32 and out.shape == ref.shape
+    if mode == "fp32":
+        assert cases.rel_err(out, ref) <= 1e-4, cases.rel_err(out, ref)
+    else:
+        assert cases.max_abs(out, ref) <= 2e-2, cases.max_abs(out, ref)
+
+
+def test_audio_projection_full_size(pkg):
+    """configs[3] shape in front of the sampler: 64 clips x 200 frames of stacked wav2vec features (12 800 rows, K = 9216) against
+    the oracle on the same device; rows are independent (a sub-batch gives the same rows), the backend is reused across calls."""
+    from oracle import fmt_oracle as O
+    from oracle.synth import synth_wav2vec_features
+    rec = dict(in_dim=9216, seed=62)
+    layer = _projection_layer(pkg, rec)
+    be = pkg.projection_backend_for(layer, DEV)
+    x = synth_wav2vec_features(64, 200, 9216, seed=5).to(DEV)
+    P = {k: v.to(DEV) for k, v in cases.projection_weights(rec).items()}
+    with torch.no_grad():
+        torch.backends.cuda.matmul.allow_tf32 = False
+        ref = O.audio_projection(P, x)
+    out = be.apply(x, "bf16")
+    assert out.shape == (64, 200, 512) and torch.isfinite(out).all()
+    assert cases.max_abs(out.cpu(), ref.cpu()) <= 2e-2
+    sub = be.apply(x[5:7], "bf16")
+    assert torch.equal(sub, out[5:7])
+    assert pkg.projection_backend_for(layer, DEV) is be and be.launch_count() >= 6
+    out32 = be.apply(x[:4], "fp32")
+    assert cases.rel_err(out32.cpu(), ref[:4].cpu()) <= 1e-4

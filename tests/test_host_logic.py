@@ -112,7 +112,13 @@ def test_node_surface_matches_reference(pkg):
     assert adv.UNIQUE_NAME == "FloatSampleMotionSequenceRD" and adv.FUNCTION == "sample_rd_sequence"
     assert list(adv.INPUT_TYPES()["required"]) == ["r_s_latent", "wa_latent", "audio_num_frames", "we_latent", "float_pipe", "a_cfg_scale",
                                                    "e_cfg_scale", "seed"]
-    assert set(pkg.NODE_CLASS_MAPPINGS) == {"FloatSampleMotionSequenceRD_VA", "FloatSampleMotionSequenceRD"}
+    # nodes_vadv.py:147-166
+    ap = pkg.FloatApplyAudioProjection
+    assert ap.UNIQUE_NAME == "FloatApplyAudioProjection" and ap.FUNCTION == "apply_projection" and ap.CATEGORY == "FLOAT/Very Advanced"
+    assert ap.RETURN_TYPES == ("TORCH_TENSOR",) and ap.RETURN_NAMES == ("wa_latent",)
+    req = ap.INPUT_TYPES()["required"]
+    assert list(req) == ["wav2vec_features", "projection_layer"] and req["projection_layer"][0] == "AUDIO_PROJECTION_LAYER"
+    assert set(pkg.NODE_CLASS_MAPPINGS) == {"FloatSampleMotionSequenceRD_VA", "FloatSampleMotionSequenceRD", "FloatApplyAudioProjection"}
 
 
 def test_node_validation_runs_before_any_device_work(pkg):
@@ -128,3 +134,21 @@ def test_node_validation_runs_before_any_device_work(pkg):
     with pytest.raises(pkg.FmtError):          # CPU target: no fallback; dropout probs restored (nodes_vadv.py:729-735)
         node.sample_rd_sequence_va(r_s, wa, we, 20, model, *args)
     assert before == (model.opt.audio_dropout_prob, model.opt.ref_dropout_prob, model.opt.emotion_dropout_prob)
+
+
+def test_audio_projection_validation_mirrors_reference(pkg):
+    """nodes_vadv.py:170-181: TypeErrors for non-tensor / non-module / wrong rank / wrong feature size, raised before any device
+    work; a CPU target has no fallback."""
+    node = pkg.FloatApplyAudioProjection()
+    layer = pkg.AudioProjectionLayer(768, 512, target_device="cpu")
+    x = torch.zeros(1, 10, 768)
+    with pytest.raises(TypeError):
+        node.apply_projection(x.numpy(), layer)
+    with pytest.raises(TypeError):
+        node.apply_projection(x, "not a module")
+    with pytest.raises(TypeError):
+        node.apply_projection(x[0], layer)
+    with pytest.raises(TypeError, match="only_last_features"):
+        node.apply_projection(torch.zeros(1, 10, 9216), layer)
+    with pytest.raises(pkg.FmtError):
+        node.apply_projection(x, layer)

@@ -7,12 +7,16 @@ import torch
 import cases
 from oracle import fmt_oracle as O
 
-FAST = [n for n, r in cases.CASES.items() if r["dims"] == "small" or r["entry"] == "cfv" or r.get("nfe", 99) <= 4]
+FAST = [n for n, r in cases.CASES.items() if r["dims"] == "small" or r["entry"] in ("cfv", "proj") or r.get("nfe", 99) <= 4]
 ALL = list(cases.CASES)
 
 
 def run_oracle(name, device="cpu", q=None, noise=None, W=None):
     rec = cases.CASES[name]
+    if rec["entry"] == "proj":      # FloatApplyAudioProjection
+        P = {k: v.to(device) for k, v in cases.projection_weights(rec).items()}
+        with torch.no_grad():
+            return O.audio_projection(P, cases.projection_input(rec).to(device))
     d = cases.dims_of(rec)
     W = W if W is not None else cases.weights(rec["dims"])
     r_s, wa, we = [t.to(device) for t in cases.case_inputs(rec)]
