@@ -1005,6 +1005,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) fmt_window_kernel(const WinPar
           WinRing rg = rings[warp];
           if (GROUPED) win_gemm2_stage(p, cx, p.gemms[g], items.it[g], sm, rg, tmem_base, epoch, (!is_edge && j == 4) ? p.b_fc1[blk] : nullptr);
           else win_gemm_stage(p, p.gemms[g], items.it[g], sm, rg, NA, tmem_base, epoch);
+          __syncwarp();                      // every lane has read rings[warp] before lane 0 overwrites it
           if (lane == 0) rings[warp] = rg;
           __syncwarp();
         } else {
