@@ -256,6 +256,40 @@ def _oracle_on_gpu(d, r_s, wa, we, T, noise, **kw):
         return O.sample_loop(Wd, d, r_s.to(DEV), wa.to(DEV), we.to(DEV), T, noise=noise.to(DEV), **kw).cpu()
 
 
+@pytest.mark.parametrize("window_flag", ["1", "2", "0"])
+def test_non_default_window_geometry(pkg, monkeypatch, window_flag):
+    """loader widgets other than the defaults (nodes_vadv_loader.py:684-704) - attention_window 4 (the
+    general band-attention code, not the 5-key fast path), 6 context frames, 1.6 s windows (L = 40) - on the full-width
+    architecture, through both schedules of the window kernel and the per-op path, against the oracle on the same device."""
+    from oracle.synth import FmtDims, synth_inputs, synth_state_dict
+    d = FmtDims(attention_window=4, num_prev_frames=6, wav2vec_sec=1.6, fmt_depth=3)
+    W = synth_state_dict(d, seed=3)
+    opt = pkg.BaseOptions()
+    for k, v in d.as_dict().items():
+        if hasattr(opt, k):
+            setattr(opt, k, v)
+    monkeypatch.setenv("FMT_WINDOW", window_flag)
+    model = pkg.FmtModel(W, opt, target_device=DEV)
+    B, T, nfe = 1, 95, 4                                            # 3 windows, ragged last one
+    r_s, wa, we = synth_inputs(d, B, T, seed=77, dynamic_we=True)
+    g = torch.Generator().manual_seed(11)
+    noise = torch.stack([torch.randn(B, d.frames_per_clip, d.dim_w, generator=g) for _ in range(3)])
+    torch.backends.cuda.matmul.allow_tf32 = False
+    Wd = {k: v.to(DEV) for k, v in W.items()}
+    with torch.no_grad():
+        ref = O.sample_loop(Wd, d, r_s.to(DEV), wa.to(DEV), we.to(DEV), T, nfe=nfe, a_cfg_scale=2.0, r_cfg_scale=1.0, e_cfg_scale=1.5,
+                            noise=noise.to(DEV)).cpu()
+    node = pkg.FloatSampleMotionSequenceRD_VA()
+    args = (2.0, 1.0, 1.5, False, nfe, "euler", 1e-5, 1e-5, 0.1, 0.1, 0.1, True, 11)
+    out, _ = node.sample_rd_sequence_va(r_s, wa, we, T, model, *args, _noise=noise)
+    assert out.shape == ref.shape == (B, T, d.dim_w)
+    assert pkg.backend_for(model, DEV).window_kernel_status() == (-1 if window_flag == "0" else 0)
+    assert cases.max_abs(out, ref) <= 2e-2, cases.max_abs(out, ref)
+    if window_flag == "0":
+        out32, _ = node.sample_rd_sequence_va(r_s, wa, we, T, model, *args, _mode="fp32", _noise=noise)
+        assert cases.rel_err(out32, ref) <= 1e-4, cases.rel_err(out32, ref)
+
+
 def test_long_clip_chained_windows(pkg):
     """BASELINE.json configs[2] in miniature: one clip, 12 sequential windows chained through prev_x / prev_wa (bf16 error
     accumulates across windows, SURVEY.md §7 'hard parts'), free-running against the oracle on the same noise."""
