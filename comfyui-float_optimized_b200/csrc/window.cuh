@@ -272,6 +272,9 @@ __device__ __forceinline__ void win_gemm_stage(const WinParams& p, const WinGemm
     rg.t_phase ^= 1;
     tc_fence_after();
     if (issuer) win_mark(p, epoch, 1);
+    // The reduce engine of one SM drains a 16 KB chunk in ~0.37 us whatever the other SMs do (measured: the same 2.25 us for
+    // the 98 KB tile with 148, 64 or 32 CTAs reducing), and it is still the fastest way out: 32 red.global.add.f32 per lane
+    // and chunk (every warp instruction one full 128-byte line) took 5.1 us for the tile, alternating LSU / TMA chunks 3.8 us.
     const int n_chunks = (p.R + 31) / 32;
     for (int c = 0; c < n_chunks; ++c) {
       float* stg = sm.stg + (c & 1) * (WIN_STG_BYTES / 4);
