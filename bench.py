@@ -142,6 +142,29 @@ def time_cpu_baseline(W, dims, B, T, budget_s, reps=3):
                 ms_per_ode_step=1e3 * best / (math.ceil(frames / L) * (NFE - 1)))
 
 
+def time_gpu_eager_baseline(W, dims, B, T, dev, reps=3):
+    """The same oracle port run eagerly on the B200 in fp32 (TF32 off): what the reference's PyTorch code does when its
+    target device is the GPU.  Reported beside the CPU baseline; never a gate."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    Wd = {k: v.to(dev) for k, v in W.items()}
+    r_s, wa, we = [t.to(dev) for t in workload_inputs(dims, B, T, 0)]
+    L = dims.frames_per_clip
+    n_win = math.ceil(T / L)
+    g = torch.Generator(dev).manual_seed(15)
+    noise = torch.stack([torch.randn(B, L, dims.dim_w, generator=g, device=dev) for _ in range(n_win)])
+    best = float("inf")
+    for i in range(reps + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cpu_reference_clip(Wd, dims, r_s, wa, we, T, noise)
+        torch.cuda.synchronize()
+        if i > 0:
+            best = min(best, time.perf_counter() - t0)
+    return dict(value=B * T / best, unit="frames/s", kind="port", device="cuda:0, torch eager fp32 (TF32 off)",
+                ms_per_ode_step=1e3 * best / (n_win * (NFE - 1)))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -305,6 +328,8 @@ def main():
                gpu_launches=int(launches), graph_kernel_nodes=be.graph_kernel_nodes(), roofline=roof, clocks=clk)
     if not args.no_cpu_baseline and world == 1:
         res["cpu_baseline"] = time_cpu_baseline(W, dims, B, T, budget_s=25.0)
+        if B <= 32:
+            res["gpu_eager_baseline"] = time_gpu_eager_baseline(W, dims, B, T, dev)
     print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()
