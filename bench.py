@@ -179,6 +179,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # oracle/synth.py only generates the seeded synthetic weights and inputs - it holds no algorithm; the oracle
+    # proper (oracle/fmt_oracle.py) is executed by the baseline legs alone (cpu_baseline, gpu_eager_baseline, --impl reference)
     from oracle.synth import FmtDims, synth_state_dict
     dims = FmtDims()
     B, T = args.batch, args.frames
