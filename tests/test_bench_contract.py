@@ -31,4 +31,4 @@ def test_algorithmic_work_matches_the_survey():
     assert abs(w["step_bytes"] - (203.4e6 + 18.43e6)) / 221.8e6 < 2e-3
     assert w["rows"] == 180
     macs_row = (w["window_flops"] / 9 / 180 - 4 * 60 * 1024) / 2
-    assert macs_row == 155_196_416 + 1024 * (1088 - 1031)      # the c_embedder K is padded 1031 -> 1088 (multiple of 64)
+    assert macs_row == 155_196_416
