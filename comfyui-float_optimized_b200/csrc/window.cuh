@@ -14,6 +14,15 @@
 //   * SIMT stages  consume the fp32 accumulators and produce the next bf16 operand: ROW (bias, gate, residual, LayerNorm,
 //                  AdaLN modulate), ATTN (band attention), GELU, COMB (CFG combine + ODE update).  Each consumer zeroes the
 //                  accumulator it has read, so the reduce-add target is clean for the next use.
+//
+// A stage lasts 4-6 us, so the kernel is written against latency, not throughput (measurements in DESIGN.md section 6):
+//   * no local memory - the barrier's ld.acquire.gpu polls are followed by CCTL.IVALL, every spill / stack slot would be
+//     re-fetched from L2 after every barrier: one inlined function, 0-byte stack, loop state that does not fit 168 registers
+//     lives in shared memory (WinCtx, WinItems, ring positions);
+//   * no integer division on the critical path - each CTA's item of every GEMM is tabulated at kernel start;
+//   * warp-uniform MMA issue loop with a handful of instructions per K block.
+// fmt_window_kernel<NV, true> is a second, experimental schedule of the same stages (one group of CTAs per sequence, N-split
+// GEMMs with roles of the UMMA operands swapped, fused GELU): see "GEMM, grouped schedule" below and DESIGN.md section 4a'.
 // Reference semantics: FMT.py:151-198 (block / decoder), :277-340 (forward), :342-401 (CFG), torchdiffeq fixed-grid solvers.
 #pragma once
 #include "kernels.cuh"
