@@ -171,12 +171,17 @@ struct WinSmem {
 };
 
 // barrier over the CTAs that share `counter` (the whole grid, or one group), entered by the main group (256 threads, named
-// barrier 1); `epoch` counts the barriers this CTA has passed (trace index), `target` = arrivals that complete this one
-__device__ __forceinline__ void win_grid_sync(const WinParams& p, unsigned& epoch, unsigned* counter, unsigned target) {
+// barrier 1).  ctr[] lives in shared memory (a register copy would be spilled, and a spill costs an L2 round trip per barrier):
+// ctr[0] = barriers this CTA has passed (trace index), ctr[which] = barriers passed on this counter; `nranks` arrivals complete one;
+// ctr[3] = evaluations finished.
+__device__ __forceinline__ void win_grid_sync(const WinParams& p, volatile unsigned* ctr, unsigned* counter, int which, unsigned nranks,
+                                              bool end_of_eval) {
   fence_proxy_async_all();                 // this thread's generic-proxy writes -> visible to later TMA (async proxy) reads
   named_bar_sync(1, WIN_MAIN);
-  ++epoch;
   if (threadIdx.x == 32) {
+    const unsigned epoch = ctr[0] + 1, target = (ctr[which] + 1) * nranks;
+    ctr[0] = epoch; ctr[which] = ctr[which] + 1;
+    if (end_of_eval) ctr[3] = ctr[3] + 1;  // evaluations finished (the loop counter of the kernel, kept out of the register file too)
     long long* tr = (p.trace != nullptr && static_cast<int>(epoch) <= p.trace_stride)
                         ? p.trace + (static_cast<size_t>(blockIdx.x) * p.trace_stride + (epoch - 1)) * 6 : nullptr;
     if (tr) tr[0] = clock64();
@@ -272,7 +277,7 @@ __device__ __forceinline__ void win_gemm_stage(const WinParams& p, const WinGemm
     rg.w_slot = w_slot; rg.w_phase = w_phase; rg.a_slot = a_slot; rg.a_phase = a_phase;
     __syncwarp();
   } else if (mw >= 4) {
-    // ===================== epilogue: TMEM (lanes = features, columns = rows) -> smem [row][feature] -> TMA reduce-add
+    // ===================== epilogue: TMEM (lanes = features, columns = rows) -> smem [row][feature] -> L2 reduce-add
     const int quarter = warp & 3;
     const int fl = quarter * 32 + lane;
     const bool issuer = (mw == 4 && lane == 0);
@@ -281,9 +286,11 @@ __device__ __forceinline__ void win_gemm_stage(const WinParams& p, const WinGemm
     rg.t_phase ^= 1;
     tc_fence_after();
     if (issuer) win_mark(p, epoch, 1);
-    // The reduce engine of one SM drains a 16 KB chunk in ~0.37 us whatever the other SMs do (measured: the same 2.25 us for
-    // the 98 KB tile with 148, 64 or 32 CTAs reducing), and it is still the fastest way out: 32 red.global.add.f32 per lane
-    // and chunk (every warp instruction one full 128-byte line) took 5.1 us for the tile, alternating LSU / TMA chunks 3.8 us.
+    // One SM's TMA write path drains a 16 KB chunk in ~0.37 us (2.25 us for the 98 KB tile) whatever the other SMs do - the same
+    // with 148, 64 or 32 CTAs reducing, the same with plain TMA stores instead of reduce-adds, and a second team of four warps
+    // feeding the engine from its own staging buffer made it slower (2.9 us).  The LSU is slower still: scalar red.global.add.f32
+    // straight from the TMEM registers (one 128-byte line per warp instruction) 5.1 us, red.global.add.v4.f32 from the staging
+    // buffer (one 512-byte tile row per warp instruction) 4.6 us.
     const int n_chunks = (p.R + 31) / 32;
     for (int c = 0; c < n_chunks; ++c) {
       float* stg = sm.stg + (c & 1) * (WIN_STG_BYTES / 4);
@@ -918,6 +925,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) fmt_window_kernel(const WinPar
   __shared__ WinParams p;
   __shared__ float red_smem[16];
   __shared__ WinItems items;
+  __shared__ unsigned bar_ctr[4];                // barriers passed: [0] total (trace index), [1] on the group counter, [2] on the grid counter
   __shared__ WinRing rings[WIN_THREADS / 32];   // ring positions of each role warp live here between GEMM stages (registers are scarce: 168 at 288 threads)
   __shared__ WinCtx cx;                  // shared, not local: a stack object is re-fetched from L2 after every grid barrier (the acquire invalidates L1)
   {
@@ -996,27 +1004,30 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) fmt_window_kernel(const WinPar
     // (grouped schedule with the GELU fused into fc1's epilogue: bs = 7, {..., 4: fc1 GEMM + GELU, 5: fc2 GEMM, 6: ROW})
     if (lane == 0) rings[warp] = WinRing();
     __syncwarp();
-    unsigned epoch = 0, n_grp = 0, n_all = 0;          // barriers passed: total / of the group / of the whole grid
-    const int D = p.depth;
-    const int bs = (GROUPED && p.fuse_gelu) ? 7 : 8;
-    const int spe = 4 + bs * D;
-    const size_t eval_stride = static_cast<size_t>(p.R) * p.NT;
-    const long long H = p.s.H;
-    for (int e = 0; e < n_eval; ++e) {
-      const __nv_bfloat16* table_e = p.table + static_cast<size_t>(e) * eval_stride;
-      int blk_ctr = 0, jj = 0;                             // block and position inside it of stage si (counted, not divided)
-      for (int si = 0; si < spe; ++si) {
+    if (threadIdx.x == 32) { bar_ctr[0] = 0; bar_ctr[1] = 0; bar_ctr[2] = 0; bar_ctr[3] = 0; }
+    named_bar_sync(1, WIN_MAIN);
+    volatile unsigned* ctr = bar_ctr;
+    // Loop invariants are re-read from shared memory (volatile) where they are used instead of living in registers across the
+    // stages: the kernel has exactly as many registers as it needs, and a spilled value costs an L2 round trip per barrier.
+    const volatile WinParams& pv = p;
+    const int bs = (GROUPED && pv.fuse_gelu) ? 7 : 8;
+    while (static_cast<int>(ctr[3]) < pv.n_steps * pv.n_stages) {
+      for (int si = 0; si < 4 + bs * pv.depth; ++si) {
+        const int e = static_cast<int>(ctr[3]);
+        const int D = pv.depth, spe = 4 + bs * D;
+        const long long H = pv.s.H;
+        const __nv_bfloat16* table_e = p.table + static_cast<size_t>(e) * (static_cast<size_t>(pv.R) * pv.NT);
         const bool is_edge = si < 2 || si >= spe - 2;
-        const int blk = blk_ctr;
-        int j = is_edge ? 0 : jj;                          // position inside the block in the 8-stage numbering
-        if (!is_edge && ++jj == bs) { jj = 0; ++blk_ctr; }
+        // block and position inside it (8-stage numbering); divisions by the CONSTANTS 8 and 7 only (shift / multiply-shift)
+        const int blk = is_edge ? 0 : (bs == 8 ? (si - 2) >> 3 : (si - 2) / 7);
+        int j = is_edge ? 0 : (bs == 8 ? (si - 2) & 7 : (si - 2) % 7);
         if (bs == 7 && j >= 5) ++j;
         const bool is_gemm = is_edge ? (si == 0 || si == spe - 2) : ((j & 1) == 0);
         if (is_gemm) {
           const int g = si == 0 ? 0 : (si == spe - 2 ? 1 + 4 * D : 1 + 4 * blk + (j >> 1));
           WinRing rg = rings[warp];
-          if (GROUPED) win_gemm2_stage(p, cx, p.gemms[g], items.it[g], sm, rg, tmem_base, epoch, (!is_edge && j == 4) ? p.b_fc1[blk] : nullptr);
-          else win_gemm_stage(p, p.gemms[g], items.it[g], sm, rg, NA, tmem_base, epoch);
+          if (GROUPED) win_gemm2_stage(p, cx, p.gemms[g], items.it[g], sm, rg, tmem_base, ctr[0], (!is_edge && j == 4) ? p.b_fc1[blk] : nullptr);
+          else win_gemm_stage(p, p.gemms[g], items.it[g], sm, rg, NA, tmem_base, ctr[0]);
           __syncwarp();                      // every lane has read rings[warp] before lane 0 overwrites it
           if (lane == 0) rings[warp] = rg;
           __syncwarp();
@@ -1028,7 +1039,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) fmt_window_kernel(const WinPar
           } else if (j == 1) {
             win_attn_dispatch(p, cx, p.b_qkv[blk]);
           } else if (j == 5) {
-            win_gelu_stage(p, cx, p.b_fc1[blk], epoch);
+            win_gelu_stage(p, cx, p.b_fc1[blk], ctr[0]);
           } else {
             const long long base = static_cast<long long>(blk) * 6 * H;
             // j == 3: after proj -> gate_msa, then the mlp modulation; j == 7: after fc2 -> gate_mlp, then the NEXT block's msa
@@ -1042,8 +1053,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) fmt_window_kernel(const WinPar
         }
         // The CFG combine reads every branch, and the next x-embedder GEMM reads what it wrote: the barriers around COMB span
         // the whole grid; every other stage only depends on rows of its own group.
-        if (!GROUPED || si >= spe - 2) { ++n_all; win_grid_sync(p, epoch, p.bar_counter, n_all * cx.all_n); }
-        else { ++n_grp; win_grid_sync(p, epoch, cx.bar, n_grp * cx.nranks); }
+        if (!GROUPED || si >= spe - 2) win_grid_sync(p, ctr, p.bar_counter, 2, cx.all_n, si == spe - 1);
+        else win_grid_sync(p, ctr, cx.bar, 1, cx.nranks, false);
       }
     }
   }
