@@ -290,7 +290,8 @@ __device__ __forceinline__ void win_gemm_stage(const WinParams& p, const WinGemm
     // with 148, 64 or 32 CTAs reducing, the same with plain TMA stores instead of reduce-adds, and a second team of four warps
     // feeding the engine from its own staging buffer made it slower (2.9 us).  The LSU is slower still: scalar red.global.add.f32
     // straight from the TMEM registers (one 128-byte line per warp instruction) 5.1 us, red.global.add.v4.f32 from the staging
-    // buffer (one 512-byte tile row per warp instruction) 4.6 us.
+    // buffer (one 512-byte tile row per warp instruction) 4.6 us; handing the last one / two / three chunks to the idle warps
+    // 1-4 as LSU reds while warps 5-8 feed the TMA path: 355 / 361 / 399 us per ODE step against 356.
     const int n_chunks = (p.R + 31) / 32;
     for (int c = 0; c < n_chunks; ++c) {
       float* stg = sm.stg + (c & 1) * (WIN_STG_BYTES / 4);
