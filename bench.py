@@ -12,7 +12,12 @@ scaling) and the step ends with one NCCL all-gather of the motion latents.
 Prints ONE JSON line (rank 0).  ``value`` = frames/s with inputs resident in HBM, timed with CUDA events, max over
 ranks; ``e2e`` = the same through the node class with CPU tensors in / CPU tensor out (H2D, noise draw, D2H inside
 the timed region); ``roofline`` = algorithmic bytes (or FLOPs) of one window launch / its measured duration against
-MEASURED_PEAKS.json; ``cpu_baseline`` = the oracle port (reference algorithm, torch fp32) on the host cores.
+MEASURED_PEAKS.json; ``cpu_baseline`` = the UNMODIFIED reference node (oracle/_ref copy, torch fp32 eager) on the host cores
+(the oracle port only when no copy of the reference exists); ``large_batch`` = configs[3] on the same GPUs: 256 clips x 200
+frames in total, 256/N clips per GPU (strong scaling of a fixed job, tensor-pipe regime) with its own roofline / e2e / clocks.
+
+The product arm imports nothing from ``oracle/``: the seeded synthetic weights and inputs come from the package's ``synth``
+module; ``oracle/`` is executed by the baseline legs alone (``cpu_baseline``, ``gpu_eager_baseline``, ``--impl reference``).
 """
 import argparse
 import json
@@ -106,39 +111,45 @@ class ClockSampler:
         return out
 
 
+def synth_module():
+    """The package's seeded synthetic weights / inputs - no algorithm of the path, nothing from oracle/."""
+    from __graft_entry__ import load_package
+    load_package()
+    return sys.modules["float_fmt_b200.synth"]
+
+
 def workload_inputs(dims, B, T, rank):
-    from oracle.synth import synth_inputs
-    return synth_inputs(dims, B, T, seed=7 + 1000 * rank)
+    return synth_module().synth_inputs(dims, B, T, seed=7 + 1000 * rank)
 
 
 def cpu_reference_clip(W, dims, r_s, wa, we, T, noise):
-    """The reference algorithm on the host cores: oracle/fmt_oracle.py (restatement pinned to the reference's fixtures)."""
+    """The reference algorithm with injected noise: oracle/fmt_oracle.py (used by the eager-GPU comparator only)."""
     from oracle import fmt_oracle as O
     with torch.no_grad():
         return O.sample_loop(W, dims, r_s, wa, we, T, nfe=NFE, a_cfg_scale=A_CFG, r_cfg_scale=R_CFG, e_cfg_scale=E_CFG, noise=noise)
 
 
 def time_cpu_baseline(W, dims, B, T, budget_s, reps=3):
-    torch.set_num_threads(os.cpu_count() or 1)
+    """The reference node itself (oracle/_ref, unmodified; port only if absent) on the host cores, on a bounded sample."""
+    from oracle import ref_arm
+    kind, run = ref_arm.make_cpu_sampler(W, dims, NFE, A_CFG, R_CFG, E_CFG)
     r_s, wa, we = workload_inputs(dims, B, T, 0)
     L = dims.frames_per_clip
-    g = torch.Generator().manual_seed(15)
     n_win = math.ceil(T / L)
-    noise = torch.stack([torch.randn(B, L, dims.dim_w, generator=g) for _ in range(n_win)])
     # bounded sample: the whole clip if one pass fits the budget, else its first window
     t0 = time.perf_counter()
-    cpu_reference_clip(W, dims, r_s, wa[:, :L], we[:, :L] if we.shape[1] > 1 else we, L, noise[:1])
+    run(r_s, wa[:, :L], we[:, :L] if we.shape[1] > 1 else we, L, 15)
     t_win = time.perf_counter() - t0
     frames, sample = (T, f"whole workload: {B} clip(s) x {T} frames, {n_win} windows x {NFE - 1} steps, 3-way CFG") \
         if t_win * n_win * (reps + 0.5) <= budget_s else (L, f"first window only: {B} clip(s) x {L} frames, {NFE - 1} steps, 3-way CFG")
     best = float("inf")
     for _ in range(reps):
         t0 = time.perf_counter()
-        cpu_reference_clip(W, dims, r_s, wa[:, :frames], we[:, :frames] if we.shape[1] > 1 else we, frames, noise[:math.ceil(frames / L)])
+        run(r_s, wa[:, :frames], we[:, :frames] if we.shape[1] > 1 else we, frames, 15)
         best = min(best, time.perf_counter() - t0)
         if best * reps > budget_s:
             break
-    return dict(value=B * frames / best, unit="frames/s", cores=torch.get_num_threads(), kind="port", sample=sample,
+    return dict(value=B * frames / best, unit="frames/s", cores=torch.get_num_threads(), kind=kind, sample=sample + "; " + ref_arm.describe(kind),
                 ms_per_ode_step=1e3 * best / (math.ceil(frames / L) * (NFE - 1)))
 
 
@@ -165,76 +176,10 @@ def time_gpu_eager_baseline(W, dims, B, T, dev, reps=3):
                 ms_per_ode_step=1e3 * best / (n_win * (NFE - 1)))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1, help="clips per GPU")
-    ap.add_argument("--frames", type=int, default=100, help="frames per clip (25 fps)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    # oracle/synth.py only generates the seeded synthetic weights and inputs - it holds no algorithm; the oracle
-    # proper (oracle/fmt_oracle.py) is executed by the baseline legs alone (cpu_baseline, gpu_eager_baseline, --impl reference)
-    from oracle.synth import FmtDims, synth_state_dict
-    dims = FmtDims()
-    B, T = args.batch, args.frames
+def measure_product(pkg, be, model, dims, B, T, rank, world, dev, dist, steps, warmup, e2e_iters):
+    """Times the product path on this rank's B clips x T frames: resident (CUDA events) and end to end (node, CPU tensors)."""
     L = dims.frames_per_clip
     n_win = math.ceil(T / L)
-    S = NFE - 1
-    workload = (f"configs[1]: {B} clip x {T} frames (4 s @25 fps), nfe={NFE}, a_cfg={A_CFG}, e_cfg={E_CFG}, 3-way CFG, euler, bf16"
-                if (B, T) == (1, 100) else f"{B} clips/GPU x {T} frames, nfe={NFE}, a_cfg={A_CFG}, e_cfg={E_CFG}, 3-way CFG, euler, bf16")
-    config = dict(workload=workload, clips_per_gpu=B, frames_per_clip=T, windows=n_win, ode_steps_per_window=S, cfg_branches=3,
-                  parallelism=f"dp{world}", l2="256 MiB memset between timed iterations (L2 flush)")
-
-    # ------------------------------------------------------------------ reference arm: the CPU port, rank 0 only
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        W = synth_state_dict(dims, seed=0)
-        torch.set_num_threads(os.cpu_count() or 1)
-        r_s, wa, we = workload_inputs(dims, B, T, 0)
-        g = torch.Generator().manual_seed(15)
-        noise = torch.stack([torch.randn(B, L, dims.dim_w, generator=g) for _ in range(n_win)])
-        t0 = time.perf_counter()
-        cpu_reference_clip(W, dims, r_s, wa[:, :L], we, L, noise[:1])
-        t_win = time.perf_counter() - t0
-        total = args.steps + args.warmup
-        frames = T if t_win * n_win * total <= 150 else L
-        sample = (f"whole workload per step ({B} clip x {T} frames)" if frames == T else
-                  f"first window per step ({B} clip x {L} frames, {S} ODE steps)") + "; oracle port of the reference (torch fp32, CPU)"
-        nw = math.ceil(frames / L)
-        for _ in range(max(0, args.warmup - 1)):
-            cpu_reference_clip(W, dims, r_s, wa[:, :frames], we, frames, noise[:nw])
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            cpu_reference_clip(W, dims, r_s, wa[:, :frames], we, frames, noise[:nw])
-        el = time.perf_counter() - t0
-        v = args.steps * B * frames / el
-        print(json.dumps(dict(impl="reference", metric="motion-latent frames/s (FMT, nfe=10)", value=v, unit="frames/s", n_gpus=args.gpus,
-                              steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * el / args.steps, higher_is_better=True, scaling="weak",
-                              vs_baseline=None, dtype="f32", data="synthetic", config=config,
-                              cpu_baseline=dict(value=v, unit="frames/s", cores=torch.get_num_threads(), kind="port", sample=sample),
-                              e2e=dict(value=v, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
-        return
-
-    # ------------------------------------------------------------------ our arm
-    from __graft_entry__ import load_package
-    pkg = load_package()
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    W = synth_state_dict(dims, seed=0)
-    model = pkg.FmtModel(W, target_device=dev)
-    be = pkg.backend_for(model, dev)
     be.configure(B, 3, False, NFE, "euler", "bf16")
     r_s, wa, we = workload_inputs(dims, B, T, rank)
     r_s_d, wa_d, we_d = r_s.to(dev), wa.to(dev), we.to(dev)
@@ -285,27 +230,27 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    clocks = ClockSampler(local_rank) if rank == 0 else None
-    for _ in range(max(3, args.warmup)):
+    clocks = ClockSampler(dev.index) if rank == 0 else None
+    for _ in range(warmup):
         step_resident()
     be.launch_count(reset=True)
-    t_res = timed(step_resident, args.steps)
+    t_res = timed(step_resident, steps)
     launches = be.launch_count(reset=True)
-    for _ in range(3):
+    for _ in range(min(3, warmup)):
         step_e2e()
-    n_e2e = max(10, args.steps // 4)
-    t_e2e = timed(step_e2e, n_e2e, wall=True)        # host-visible latency: the call returns a CPU tensor
+    t_e2e = timed(step_e2e, e2e_iters, wall=True)        # host-visible latency: the call returns a CPU tensor
     clk = clocks.stop() if clocks else None
+    h2d = (r_s.numel() + wa.numel() + we.numel()) * 4
+    d2h = B * T * dims.dim_w * 4
+    del flush, gathered, out_d, noise_d
+    return dict(t_step=t_res / steps, t_e2e=t_e2e / e2e_iters, launches=int(launches), clocks=clk, h2d=h2d, d2h=d2h, n_win=n_win,
+                window_kernel=be.window_kernel_status())
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    pk = peaks()
+
+def roofline_record(dims, B, T, t_step, n_win, pk):
+    S = NFE - 1
     work = algorithmic_work(dims, B, 3, S)
-    t_step = t_res / args.steps
     t_window = t_step / n_win
-    frames_total = world * B * T
     hbm_achieved = work["window_bytes"] / t_window / 1e9
     tf_achieved = work["window_flops"] / t_window / 1e12
     hbm_frac, tf_frac = hbm_achieved / pk["hbm_gbs"], tf_achieved / pk["bf16_tflops_sustained"]
@@ -320,14 +265,114 @@ def main():
                 traffic_source=prof.get("source"),
                 us_per_ode_step=1e6 * t_window / S, algorithmic_bytes_per_window=work["window_bytes"],
                 algorithmic_flops_per_window=work["window_flops"], other_bound_frac=min(hbm_frac, tf_frac))
-    h2d = (r_s.numel() + wa.numel() + we.numel()) * 4
-    d2h = B * T * dims.dim_w * 4
+    return roof
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="clips per GPU")
+    ap.add_argument("--frames", type=int, default=100, help="frames per clip (25 fps)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--large-clips", type=int, default=256, help="total clips of the large_batch record (configs[3]); 0 = skip it")
+    ap.add_argument("--large-frames", type=int, default=200)
+    ap.add_argument("--force-port", action="store_true", help="reference arm: time the oracle port even when the reference copy exists")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    synth = synth_module()
+    dims = synth.FmtDims()
+    B, T = args.batch, args.frames
+    L = dims.frames_per_clip
+    n_win = math.ceil(T / L)
+    S = NFE - 1
+    workload = (f"configs[1]: {B} clip x {T} frames (4 s @25 fps), nfe={NFE}, a_cfg={A_CFG}, e_cfg={E_CFG}, 3-way CFG, euler, bf16"
+                if (B, T) == (1, 100) else f"{B} clips/GPU x {T} frames, nfe={NFE}, a_cfg={A_CFG}, e_cfg={E_CFG}, 3-way CFG, euler, bf16")
+    config = dict(workload=workload, clips_per_gpu=B, frames_per_clip=T, windows=n_win, ode_steps_per_window=S, cfg_branches=3,
+                  parallelism=f"dp{world}", l2="256 MiB memset between timed iterations (L2 flush)")
+
+    # ------------------------------------------------------------------ reference arm: the reference node on the host cores, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import ref_arm
+        W = synth.synth_state_dict(dims, seed=0)
+        kind, run = ref_arm.make_cpu_sampler(W, dims, NFE, A_CFG, R_CFG, E_CFG, force_port=args.force_port)
+        r_s, wa, we = workload_inputs(dims, B, T, 0)
+        t0 = time.perf_counter()
+        run(r_s, wa[:, :L], we, L, 15)
+        t_win = time.perf_counter() - t0
+        total = args.steps + args.warmup
+        frames = T if t_win * n_win * total <= 150 else L
+        sample = (f"whole workload per step ({B} clip x {T} frames)" if frames == T else
+                  f"first window per step ({B} clip x {L} frames, {S} ODE steps)") + "; " + ref_arm.describe(kind)
+        for _ in range(max(0, args.warmup - 1)):
+            run(r_s, wa[:, :frames], we, frames, 15)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            run(r_s, wa[:, :frames], we, frames, 15)
+        el = time.perf_counter() - t0
+        v = args.steps * B * frames / el
+        print(json.dumps(dict(impl="reference", metric="motion-latent frames/s (FMT, nfe=10)", value=v, unit="frames/s", n_gpus=args.gpus,
+                              steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * el / args.steps, higher_is_better=True, scaling="weak",
+                              vs_baseline=None, dtype="f32", data="synthetic", config=config, cpu_processes=1,
+                              cpu_baseline=dict(value=v, unit="frames/s", cores=torch.get_num_threads(), kind=kind, sample=sample),
+                              e2e=dict(value=v, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    W = synth.synth_state_dict(dims, seed=0)
+    model = pkg.FmtModel(W, target_device=dev)
+    be = pkg.backend_for(model, dev)
+    pk = peaks()
+
+    m = measure_product(pkg, be, model, dims, B, T, rank, world, dev, dist, args.steps, max(3, args.warmup), max(10, args.steps // 4))
+    graph_nodes = be.graph_kernel_nodes()
+
+    # ---- configs[3]: a fixed job of 256 clips x 200 frames split over the GPUs (strong scaling; tensor-pipe regime)
+    large = None
+    if args.large_clips > 0:
+        Bl, Tl = -(-args.large_clips // world), args.large_frames
+        try:
+            ml = measure_product(pkg, be, model, dims, Bl, Tl, rank, world, dev, dist, 3, 3, 3)
+            roof_l = roofline_record(dims, Bl, Tl, ml["t_step"], ml["n_win"], pk)
+            large = dict(workload=f"configs[3]: {world * Bl} clips x {Tl} frames in total, {Bl} clips per GPU, nfe={NFE}, 3-way CFG, euler, bf16",
+                         clips_total=world * Bl, clips_per_gpu=Bl, frames_per_clip=Tl, scaling="strong (fixed 256-clip job)",
+                         value=world * Bl * Tl / ml["t_step"], unit="frames/s", ms_per_step=1e3 * ml["t_step"], steps=3, warmup=3,
+                         us_per_ode_step=roof_l["us_per_ode_step"], roofline=roof_l, gpu_launches=ml["launches"], clocks=ml["clocks"],
+                         e2e=dict(value=world * Bl * Tl / ml["t_e2e"], unit="frames/s", h2d_bytes_per_step=ml["h2d"], d2h_bytes_per_step=ml["d2h"],
+                                  ms_per_step=1e3 * ml["t_e2e"]))
+        except Exception as e:          # e.g. not enough free HBM for the 256-clip tables next to another tenant
+            large = dict(error=f"{type(e).__name__}: {e}"[:300])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    t_step = m["t_step"]
+    frames_total = world * B * T
+    roof = roofline_record(dims, B, T, t_step, n_win, pk)
     res = dict(metric="motion-latent frames/s (FMT, nfe=10)", value=frames_total / t_step, unit="frames/s", n_gpus=world, steps=args.steps,
                warmup=max(3, args.warmup), ms_per_step=1e3 * t_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
-               data="synthetic", config=config, us_per_ode_step=1e6 * t_window / S,
-               e2e=dict(value=frames_total / (t_e2e / n_e2e), unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                        ms_per_step=1e3 * t_e2e / n_e2e, api="FloatSampleMotionSequenceRD_VA.sample_rd_sequence_va (CPU tensors in/out)"),
-               gpu_launches=int(launches), graph_kernel_nodes=be.graph_kernel_nodes(), roofline=roof, clocks=clk)
+               data="synthetic", config=config, us_per_ode_step=roof["us_per_ode_step"],
+               e2e=dict(value=frames_total / m["t_e2e"], unit="frames/s", h2d_bytes_per_step=m["h2d"], d2h_bytes_per_step=m["d2h"],
+                        ms_per_step=1e3 * m["t_e2e"], api="FloatSampleMotionSequenceRD_VA.sample_rd_sequence_va (CPU tensors in/out)"),
+               gpu_launches=m["launches"], graph_kernel_nodes=graph_nodes, window_kernel_status=m["window_kernel"], roofline=roof, clocks=m["clocks"])
+    if large is not None:
+        res["large_batch"] = large
     if not args.no_cpu_baseline and world == 1:
         res["cpu_baseline"] = time_cpu_baseline(W, dims, B, T, budget_s=25.0)
         if B <= 32:

@@ -3,17 +3,17 @@ the reference nodes they replace, backed by libfmt_b200.so instead of eager PyTo
 
   FloatSampleMotionSequenceRD_VA   <- src/nodes/nodes_vadv.py:534-735
   FloatSampleMotionSequenceRD      <- src/nodes/nodes_adv.py:697-820
-The simple node ``FLOAT Process (Opt)`` (nodes.py:146-222) reaches this backend through ``sampler.float_sample``,
-which replaces the body of ``FLOAT.sample`` (FLOAT.py:172-253); see INTEGRATION.md for the two-line patch.
+  FloatProcess ("FLOAT Process (Opt)") <- src/nodes/nodes.py:146-222: same node; for the duration of the call the pipe's
+                                      ``G.sample`` (FLOAT.py:172-253) is this backend, everything else (face crop, wav2vec /
+                                      SER encoders, image encoder / decoder) stays the reference code of the pipe.
 Tensors cross node edges on the CPU, as in the reference (nodes_vadv.py:197,719).
 """
 import logging
-from contextlib import contextmanager
 
 import torch
 
 from .options import BaseOptions, TORCHDIFFEQ_FIXED_STEP_SOLVERS
-from .sampler import perform_ode_sampling_loop
+from .sampler import PRECISION_MODES, perform_ode_sampling_loop, resolve_mode, use_b200_sampler
 
 NODES_NAME = "FLOAT_Optimized"
 logger = logging.getLogger(f"{NODES_NAME}.b200_fmt")
@@ -22,21 +22,24 @@ try:  # ComfyUI progress bar, one tick per window (nodes_adv.py:600,688)
     import comfy.utils as _comfy_utils
 except Exception:  # not running under ComfyUI
     _comfy_utils = None
-try:  # VRAM manager used by the reference around the sampling call (nodes_vadv.py:697)
-    from seconohe.torch import model_to_target as _model_to_target
-except Exception:
-    _model_to_target = None
 
 
 def _progress_bar(total):
     return _comfy_utils.ProgressBar(total) if _comfy_utils is not None else None
 
 
-@contextmanager
-def _weights_context(fmt_model):
-    """The packed bf16 weights live in the backend, so the nn.Module does not have to move to the GPU; when the
-    reference's VRAM manager exists and the module is a real nn.Module we still honour it (it only offloads after)."""
-    yield
+# Optional widget both sampler nodes add to the reference's inputs (everything else is identical).  "default" = the FMT_MODE
+# environment variable, else bf16.  The reference computes in fp32: "fp32" reproduces it to 1e-4 relative (and passes the
+# PSNR >= 40 dB decoded-frame gate); "bf16" is ~10x faster and within 2e-2 max-abs of the reference latents, which a
+# RANDOM-INIT decoder turns into 20-35 dB (profiles/r02_psnr.json) - see README.md "Precision".
+PRECISION_WIDGET = (("default",) + PRECISION_MODES, {"default": "default", "tooltip": "GEMM operand precision: bf16 (fast, tcgen05) or fp32 "
+                                                     "(validation mode, matches the reference to 1e-4). default = $FMT_MODE or bf16."})
+
+
+def _active_mode(precision, _mode):
+    mode = resolve_mode(_mode if _mode is not None else precision)
+    logger.info(f"B200 FMT sampler: precision mode {mode}")
+    return mode
 
 
 class FloatSampleMotionSequenceRD_VA:
@@ -69,7 +72,8 @@ class FloatSampleMotionSequenceRD_VA:
                 "emotion_dropout_prob": ("FLOAT", {"default": o.emotion_dropout_prob, "min": 0.0, "max": 1.0, "step": 0.01}),
                 "fix_noise_seed": ("BOOLEAN", {"default": o.fix_noise_seed}),
                 "seed": ("INT", {"default": o.seed, "min": 0, "max": 0xffffffffffffffff}),
-            }
+            },
+            "optional": {"precision": PRECISION_WIDGET},
         }
 
     RETURN_TYPES = ("TORCH_TENSOR", "FLOAT_FMT_MODEL")
@@ -79,7 +83,7 @@ class FloatSampleMotionSequenceRD_VA:
     def sample_rd_sequence_va(self, r_s_latent, wa_latent, we_latent, audio_num_frames, float_fmt_model,
                               a_cfg_scale, r_cfg_scale, e_cfg_scale, include_r_cfg, nfe, torchdiffeq_ode_method,
                               ode_atol, ode_rtol, audio_dropout_prob, ref_dropout_prob, emotion_dropout_prob,
-                              fix_noise_seed, seed, _mode="bf16", _noise=None):
+                              fix_noise_seed, seed, precision="default", _mode=None, _noise=None):
         # window geometry from the options the FMT was built with (nodes_vadv.py:627-645)
         src = BaseOptions()
         fco = getattr(float_fmt_model, "final_construction_options", None)
@@ -116,15 +120,15 @@ class FloatSampleMotionSequenceRD_VA:
                 noise_gen.manual_seed(seed)
             r_s_dev, wa_dev, we_dev = r_s_latent.to(target_device), wa_latent.to(target_device), we_latent.to(target_device)
             n_windows = -(-int(audio_num_frames) // frames_for_clip)
-            with _weights_context(float_fmt_model):
-                r_d = perform_ode_sampling_loop(
-                    fmt_model=float_fmt_model, r_s_latent_dev=r_s_dev, wa_latent_dev=wa_dev, we_latent_dev=we_dev,
-                    audio_num_frames=audio_num_frames, model_num_prev_frames=num_prev, model_num_frames_for_clip=frames_for_clip,
-                    model_dim_w=dim_w, ode_nfe=nfe, ode_method=torchdiffeq_ode_method, ode_atol=ode_atol, ode_rtol=ode_rtol,
-                    target_device=target_device, a_cfg_scale=a_cfg_scale, r_cfg_scale=r_cfg_scale, e_cfg_scale=e_cfg_scale,
-                    include_r_cfg=include_r_cfg, noise_seed_generator=noise_gen, progress_bar=_progress_bar(n_windows),
-                    mode=_mode, noise=_noise)
-                r_d_cpu = r_d.cpu()
+            # the packed weights live in the backend (sampler.backend_for), so the nn.Module never has to move to the GPU
+            r_d = perform_ode_sampling_loop(
+                fmt_model=float_fmt_model, r_s_latent_dev=r_s_dev, wa_latent_dev=wa_dev, we_latent_dev=we_dev,
+                audio_num_frames=audio_num_frames, model_num_prev_frames=num_prev, model_num_frames_for_clip=frames_for_clip,
+                model_dim_w=dim_w, ode_nfe=nfe, ode_method=torchdiffeq_ode_method, ode_atol=ode_atol, ode_rtol=ode_rtol,
+                target_device=target_device, a_cfg_scale=a_cfg_scale, r_cfg_scale=r_cfg_scale, e_cfg_scale=e_cfg_scale,
+                include_r_cfg=include_r_cfg, noise_seed_generator=noise_gen, progress_bar=_progress_bar(n_windows),
+                mode=_active_mode(precision, _mode), noise=_noise)
+            r_d_cpu = r_d.cpu()
             return (r_d_cpu, float_fmt_model)
         except Exception as e:
             logger.error(f"Error during VA ODE sampling: {e}")
@@ -151,7 +155,8 @@ class FloatSampleMotionSequenceRD:
                 "a_cfg_scale": ("FLOAT", {"default": 2.0, "min": 0.0, "max": 10.0, "step": 0.1}),
                 "e_cfg_scale": ("FLOAT", {"default": 1.0, "min": 0.0, "max": 10.0, "step": 0.1}),
                 "seed": ("INT", {"default": 62064758300528, "min": 0, "max": 0xffffffffffffffff}),
-            }
+            },
+            "optional": {"precision": PRECISION_WIDGET},
         }
 
     RETURN_TYPES = ("TORCH_TENSOR", "FLOAT_PIPE")
@@ -159,7 +164,7 @@ class FloatSampleMotionSequenceRD:
     FUNCTION = "sample_rd_sequence"
 
     def sample_rd_sequence(self, r_s_latent, wa_latent, audio_num_frames, we_latent, float_pipe, a_cfg_scale, e_cfg_scale, seed,
-                           _mode="bf16", _noise=None):
+                           precision="default", _mode=None, _noise=None):
         agent = float_pipe
         opt = agent.opt
         if not all(isinstance(t, torch.Tensor) for t in [r_s_latent, wa_latent, we_latent]):
@@ -188,12 +193,79 @@ class FloatSampleMotionSequenceRD:
             model_num_frames_for_clip=agent.G.num_frames_for_clip, model_dim_w=opt.dim_w, ode_nfe=opt.nfe,
             ode_method=opt.torchdiffeq_ode_method, ode_atol=opt.ode_atol, ode_rtol=opt.ode_rtol, target_device=device,
             a_cfg_scale=a_cfg_scale, r_cfg_scale=opt.r_cfg_scale, e_cfg_scale=e_cfg_scale, include_r_cfg=False,
-            noise_seed_generator=noise_gen, progress_bar=_progress_bar(n_windows), mode=_mode, noise=_noise)
+            noise_seed_generator=noise_gen, progress_bar=_progress_bar(n_windows), mode=_active_mode(precision, _mode), noise=_noise)
         return (r_d.cpu(), float_pipe)
+
+
+EMOTIONS = ['none', 'angry', 'disgust', 'fear', 'happy', 'neutral', 'sad', 'surprise']     # nodes.py:27
+
+try:  # VRAM manager the reference wraps the call in (nodes.py:171); absent outside ComfyUI + seconohe
+    from seconohe.torch import model_to_target as _model_to_target
+except Exception:
+    _model_to_target = None
+
+
+class FloatProcess:
+    UNIQUE_NAME = "FloatProcessOpt"
+    DISPLAY_NAME = "FLOAT Process (Opt)"
+    DESCRIPTION = "Float Processing"
+    CATEGORY = "FLOAT"
+
+    @classmethod
+    def INPUT_TYPES(cls):
+        return {
+            "required": {
+                "ref_image": ("IMAGE",),
+                "ref_audio": ("AUDIO",),
+                "float_pipe": ("FLOAT_PIPE",),
+                "a_cfg_scale": ("FLOAT", {"default": 2.0, "min": 1.0, "step": 0.1}),
+                "e_cfg_scale": ("FLOAT", {"default": 1.0, "min": 1.0, "step": 0.1}),
+                "fps": ("FLOAT", {"default": 25, "step": 1}),
+                "emotion": (EMOTIONS, {"default": "none"}),
+                "face_align": ("BOOLEAN", {"default": True},),
+                "seed": ("INT", {"default": 62064758300528, "min": 0, "max": 0xffffffffffffffff}),
+            },
+            "optional": {"precision": PRECISION_WIDGET},
+        }
+
+    RETURN_TYPES = ("IMAGE", "AUDIO", "FLOAT")
+    RETURN_NAMES = ("images", "ref_audio", "fps")
+    FUNCTION = "floatprocess"
+
+    def floatprocess(self, ref_image, ref_audio, float_pipe, a_cfg_scale, e_cfg_scale, fps, emotion, face_align, seed,
+                     precision="default", _mode=None):
+        """One (image, audio) pair at a time, the shorter batch repeating its last item, seed + i per pair - as nodes.py:169-222;
+        the motion latents of every pair come from libfmt_b200.so instead of eager PyTorch + torchdiffeq."""
+        import contextlib
+        pipe = float_pipe
+        pipe.G.target_device = pipe.rank
+        pipe.G.cudnn_benchmark_setting = pipe.opt.cudnn_benchmark_enabled
+        vram = _model_to_target(logger, pipe.G) if _model_to_target is not None else contextlib.nullcontext()
+        mode = _active_mode(precision, _mode)
+        with vram, use_b200_sampler(pipe.G, mode):
+            pipe.opt.fps = fps
+            wave, rate = ref_audio["waveform"], ref_audio["sample_rate"]
+            n_img, n_aud = ref_image.shape[0], wave.shape[0]
+            n = max(n_img, n_aud)
+            frames, waves = [], []
+            for i in range(n):
+                img = ref_image[min(i, n_img - 1):min(i, n_img - 1) + 1].to(pipe.rank)
+                wav = wave[min(i, n_aud - 1):min(i, n_aud - 1) + 1].to(pipe.rank)
+                out = pipe.run_inference(None, img, {"waveform": wav, "sample_rate": rate}, a_cfg_scale=a_cfg_scale,
+                                         r_cfg_scale=pipe.opt.r_cfg_scale, e_cfg_scale=e_cfg_scale,
+                                         emo=None if emotion == "none" else emotion, no_crop=not face_align, seed=seed + i)
+                frames.append(out.cpu())
+                waves.append(wav.cpu())
+        if n == 1:
+            audio_out = ref_audio
+        else:   # the audio of every pair, concatenated along time (nodes.py:213-220)
+            cat = torch.cat([w.squeeze(0) for w in waves], dim=1).unsqueeze(0).to(wave.device)
+            audio_out = {"waveform": cat, "sample_rate": rate}
+        return (torch.cat(frames, dim=0), audio_out, fps)
 
 
 from .audio import FloatApplyAudioProjection  # noqa: E402  (SURVEY.md §8f rank 2: the node in front of the sampler)
 
-NODE_CLASSES = [FloatSampleMotionSequenceRD_VA, FloatSampleMotionSequenceRD, FloatApplyAudioProjection]
+NODE_CLASSES = [FloatSampleMotionSequenceRD_VA, FloatSampleMotionSequenceRD, FloatProcess, FloatApplyAudioProjection]
 NODE_CLASS_MAPPINGS = {c.UNIQUE_NAME: c for c in NODE_CLASSES}
 NODE_DISPLAY_NAME_MAPPINGS = {c.UNIQUE_NAME: c.DISPLAY_NAME for c in NODE_CLASSES}

