@@ -6,6 +6,7 @@
 #include "../../include/fmt_b200.h"
 #include "kernels.cuh"
 #include "window.cuh"
+#include "flow.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -91,8 +92,16 @@ struct FmtHandle {
   size_t ws_bytes = 0;
 
   // persistent window kernel (window.cuh): used when the plan has <= 256 token rows in bf16 mode
-  int use_window = 1;                            // FMT_WINDOW: 0 = one kernel per op, 1 = split-K window kernel, 2 = grouped window kernel
+  int use_window = 3;                            // FMT_WINDOW: 0 = one kernel per op, 1 = barrier-stepped split-K window kernel, 2 = grouped one, 3 = dataflow kernel (flow.cuh)
   bool window_active = false;
+  // dataflow window kernel (flow.cuh)
+  bool flow_active = false;
+  int flow_ch = 64;                              // rows per chunk (FMT_FLOW_CH = 32 | 64)
+  int flow_max_rows = 256;                       // plans with more token rows run one kernel per op (FMT_FLOW_MAX_ROWS)
+  int flow_gelu_f4 = 2;                          // float4 per thread and GELU unit (FMT_FLOW_GELU_F4 = 1..4)
+  long long flow_spin_limit = 4000000000ll;      // SM clocks a wait may spin before the kernel traps (FMT_FLOW_SPIN_MS)
+  FlowParams flow_params{};
+  DevBuf flow_gemms, flow_tmaps, flow_acc, flow_act, flow_flags, flow_trace;
   bool win_grouped = false;                      // the active plan runs fmt_window_kernel<NV, true>
   int win_spg = 1;                               // sequences per group (FMT_WIN_SPG), rows per group = spg * N <= 128
   int win_fuse_gelu = 1;                         // FMT_WIN_FUSE_GELU=0 keeps the separate GELU stage in the grouped schedule
@@ -584,6 +593,172 @@ static int launch_window(FmtHandle* h, cudaStream_t st) {
   return set_err(-1, "window kernel: dim_h %d unsupported", h->shape.H);
 }
 
+// ------------------------------------------------------------------------------------------------ dataflow window kernel (flow.cuh)
+static bool flow_eligible(const FmtHandle* h, const FmtPlan* p) {
+  const FmtDims& d = h->d;
+  const int N = d.num_prev_frames + d.frames_per_clip;
+  const int R = p->n_branches * p->batch * N;
+  const int nv = d.dim_h / 128;
+  const int CH = h->flow_ch;
+  const int nsub = (N + CH - 1) / CH;
+  const int hd = d.dim_h / (d.num_heads > 0 ? d.num_heads : 1);
+  return h->use_window == 3 && p->mode == FMT_MODE_BF16 && R <= h->flow_max_rows && p->n_steps * p->n_stages >= 1 && d.depth <= WIN_MAX_DEPTH &&
+         d.dim_h % 128 == 0 && (nv == 1 || nv == 2 || nv == 4 || nv == 8) && d.mlp_hidden % 64 == 0 && d.dim_w % 64 == 0 &&
+         (hd == 32 || hd == 64 || hd == 128) && p->n_branches * p->batch * nsub <= FLOW_MAX_CHUNKS && d.attention_window <= CH &&
+         p->n_steps * p->n_stages < 256 && 2 + 4 * d.depth < 256;
+}
+
+static int setup_flow(FmtHandle* h, cudaStream_t st) {
+  const ModelShape& s = h->shape;
+  const FmtDims& d = h->d;
+  const int R = h->R, H = s.H, M4 = d.mlp_hidden, W = s.W, D = d.depth;
+  const int n_gemms = 2 + 4 * D;
+  const int grid = h->num_sms;
+  const int CH = h->flow_ch;
+  FlowParams& fp = h->flow_params;
+  fp = FlowParams{};
+  fp.s = s; fp.R = R; fp.depth = D; fp.heads = d.num_heads; fp.window = d.attention_window; fp.mlp_hidden = M4; fp.NT = h->NT;
+  fp.n_steps = h->plan.n_steps; fp.n_stages = h->plan.n_stages; fp.n_gemms = n_gemms;
+  fp.CH = CH; fp.nsub = (s.N + CH - 1) / CH; fp.NPs = fp.nsub * CH; fp.n_chunks = s.nb * s.B * fp.nsub; fp.RP = fp.n_chunks * CH;
+  fp.n_tslots = 512 / CH;
+  fp.gelu_f4 = h->flow_gelu_f4 < 1 ? 1 : h->flow_gelu_f4 > 4 ? 4 : h->flow_gelu_f4;
+  fp.spin_limit = h->flow_spin_limit;
+  const size_t RP = fp.RP;
+
+  // fp32 arena, zeroed before every launch: X | Pacc | QKVacc x 2 | Hacc | Vacc, padded rows
+  const size_t n_x = RP * H, n_q = RP * 3 * H, n_h = RP * M4, n_v = RP * W;
+  FMT_OK(dev_alloc(h, h->flow_acc, (2 * n_x + 2 * n_q + n_h + n_v) * 4));
+  float* arena = static_cast<float*>(h->flow_acc.p);
+  fp.X = arena; fp.Pacc = fp.X + n_x; fp.QKVacc = fp.Pacc + n_x; fp.Hacc = fp.QKVacc + 2 * n_q; fp.Vacc = fp.Hacc + n_h;
+  // pre-tiled operands [chunk][K block][CH][64] bf16, zero-filled once (rows past a chunk's valid rows are never written)
+  const size_t t_a1 = static_cast<size_t>(fp.n_chunks) * (H / 64) * CH * 64, t_hm = static_cast<size_t>(fp.n_chunks) * (M4 / 64) * CH * 64;
+  FMT_OK(dev_alloc(h, h->flow_act, (2 * t_a1 + t_hm) * sizeof(bf16)));
+  CUDA_OK(cudaMemsetAsync(h->flow_act.p, 0, h->flow_act.bytes, st));
+  fp.A1 = static_cast<bf16*>(h->flow_act.p); fp.A2 = fp.A1 + t_a1; fp.Hm = fp.A2 + t_a1; fp.ax = static_cast<bf16*>(h->ax.p);
+  fp.table = static_cast<const bf16*>(h->table.p);
+  fp.b_x = h->x_emb.b; fp.pos = h->pos; fp.b_dec = h->dec.b;
+  for (int i = 0; i < D; ++i) { fp.b_qkv[i] = h->qkv[i].b; fp.b_proj[i] = h->proj[i].b; fp.b_fc1[i] = h->fc1[i].b; fp.b_fc2[i] = h->fc2[i].b; }
+  fp.x_state = static_cast<float*>(h->xstate.p); fp.kbuf = static_cast<float*>(h->kbuf.p); fp.ddt = static_cast<const float*>(h->ddt.p);
+  for (int i = 0; i < h->plan.n_stages * h->plan.n_stages; ++i) fp.rk_a[i] = h->rk_a[i];
+  for (int i = 0; i < h->plan.n_stages; ++i) fp.rk_b[i] = h->rk_b[i];
+  fp.wargs = static_cast<const WindowArgs*>(h->wargs.p);
+  // release counters: [n_eval][n_gemms][n_chunks] for the GEMM engine and the same for the SIMT engine
+  const size_t n_flags = static_cast<size_t>(h->n_eval) * n_gemms * fp.n_chunks * FLOW_FLAG_STRIDE;
+  FMT_OK(dev_alloc(h, h->flow_flags, (2 * n_flags + 2 * FLOW_FLAG_STRIDE) * sizeof(unsigned)));   // + the two rendezvous counters of the trace mode
+  fp.g_done = static_cast<unsigned*>(h->flow_flags.p); fp.s_done = fp.g_done + n_flags;
+  if (!h->win_err_host) {
+    CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&h->win_err_host), sizeof(int), cudaHostAllocMapped));
+    *h->win_err_host = 0;
+    CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->win_err_dev), h->win_err_host, 0));
+  }
+  fp.err_flag = h->win_err_dev;
+  fp.trace = nullptr; fp.trace_eval = -1;
+  if (getenv("FMT_WIN_TRACE") && atoi(getenv("FMT_WIN_TRACE")) != 0) {
+    FMT_OK(dev_alloc(h, h->flow_trace, (static_cast<size_t>(grid) * 2 * n_gemms * fp.n_chunks * 8 + static_cast<size_t>(grid) * 4) * sizeof(long long)));
+    CUDA_OK(cudaMemsetAsync(h->flow_trace.p, 0, h->flow_trace.bytes, st));
+    fp.trace = static_cast<long long*>(h->flow_trace.p);
+    fp.trace_eval = h->n_eval / 2;
+    if (const char* e = getenv("FMT_WIN_TRACE_EVAL")) fp.trace_eval = atoi(e);
+  }
+
+  // tensor maps: one per GEMM (weights) + ax + accumulators (Pacc, QKVacc parity 0 / 1, Hacc, Vacc)
+  const int TM_AX = n_gemms, C_P = n_gemms + 1, C_Q = n_gemms + 2, C_H = n_gemms + 4, C_V = n_gemms + 5, n_maps = n_gemms + 6;
+  std::vector<CUtensorMap> maps(n_maps);
+  std::vector<FlowGemm> gemms(n_gemms);
+  const CUtensorMapDataType BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  FMT_OK(make_tmap_ex(h, &maps[TM_AX], fp.ax, BF, 2, R, W, W, 64, CH, CU_TENSOR_MAP_SWIZZLE_128B));
+  FMT_OK(make_tmap_ex(h, &maps[C_P], fp.Pacc, F32, 4, fp.RP, H, H, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
+  FMT_OK(make_tmap_ex(h, &maps[C_Q], fp.QKVacc, F32, 4, fp.RP, 3 * H, 3 * H, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
+  FMT_OK(make_tmap_ex(h, &maps[C_Q + 1], fp.QKVacc + n_q, F32, 4, fp.RP, 3 * H, 3 * H, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
+  FMT_OK(make_tmap_ex(h, &maps[C_H], fp.Hacc, F32, 4, fp.RP, M4, M4, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
+  FMT_OK(make_tmap_ex(h, &maps[C_V], fp.Vacc, F32, 4, fp.RP, W, W, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
+  fp.tm_ax = TM_AX;
+
+  int next_off = 0, max_nk = 1;
+  auto plan_gemm = [&](int g, const Linear& L, int a_src, int tm_acc, int pk_override, int par_blk) -> int {
+    FlowGemm& G = gemms[g];
+    G.tm_w = g; G.tm_acc = tm_acc; G.a_src = a_src; G.par_blk = par_blk;
+    G.n_ft = (L.N + 127) / 128;
+    G.nkb = (L.K + 63) / 64;
+    REQUIRE(G.n_ft <= grid, "flow kernel: %d feature tiles > %d SMs", G.n_ft, grid);
+    int pk = grid / G.n_ft;
+    if (pk > G.nkb) pk = G.nkb;
+    if (pk_override > 0 && pk_override <= pk) pk = pk_override;
+    while ((G.nkb + pk - 1) / pk > FLOW_MAX_NW - 1 && pk < G.nkb) ++pk;      // an item's weight tiles must fit the ring
+    REQUIRE((G.nkb + pk - 1) / pk <= FLOW_MAX_NW - 1 && G.n_ft * pk <= grid, "flow kernel: K = %d does not fit the weight ring", L.K);
+    G.pk = pk;
+    G.n_items = G.n_ft * pk;
+    G.cta_off = next_off;
+    next_off = (next_off + G.n_items) % grid;
+    const int nk = (G.nkb + pk - 1) / pk;
+    if (nk > max_nk) max_nk = nk;
+    return make_tmap_ex(h, &maps[g], L.w16, BF, 2, L.N, L.K, L.K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+  };
+  FMT_OK(plan_gemm(0, h->x_emb, 0, C_P, 0, -1));
+  for (int i = 0; i < D; ++i) {
+    FMT_OK(plan_gemm(1 + 4 * i, h->qkv[i], 1, C_Q, h->win_pk[0], i));
+    FMT_OK(plan_gemm(2 + 4 * i, h->proj[i], 2, C_P, h->win_pk[1], -1));
+    FMT_OK(plan_gemm(3 + 4 * i, h->fc1[i], 1, C_H, h->win_pk[2], -1));
+    FMT_OK(plan_gemm(4 + 4 * i, h->fc2[i], 3, C_P, h->win_pk[3], -1));
+  }
+  FMT_OK(plan_gemm(1 + 4 * D, h->dec, 1, C_V, 0, -1));
+  // shared memory: 2 staging tiles + activation ring (slots of the largest item's K range) + weight ring with what is left
+  fp.a_slot_bytes = max_nk * CH * 128;
+  fp.na = CH <= 32 ? 3 : 2;
+  if (const char* e = getenv("FMT_FLOW_NA")) { const int v = atoi(e); if (v >= 2 && v <= FLOW_MAX_NA) fp.na = v; }
+  const int left = FLOW_SMEM_MAX - 1024 - FLOW_BAR_BYTES - 2 * FLOW_STG_BYTES - fp.na * fp.a_slot_bytes;
+  fp.nw = left / FLOW_W_BYTES;
+  if (fp.nw > FLOW_MAX_NW) fp.nw = FLOW_MAX_NW;
+  if (const char* e = getenv("FMT_FLOW_NW")) { const int v = atoi(e); if (v >= 2 && v <= fp.nw) fp.nw = v; }
+  REQUIRE(fp.nw >= max_nk + 1, "flow kernel: weight ring of %d slots cannot hold an item of %d K blocks", fp.nw, max_nk);
+
+  FMT_OK(dev_alloc(h, h->flow_gemms, gemms.size() * sizeof(FlowGemm)));
+  FMT_OK(dev_alloc(h, h->flow_tmaps, maps.size() * sizeof(CUtensorMap)));
+  CUDA_OK(cudaMemcpyAsync(h->flow_gemms.p, gemms.data(), gemms.size() * sizeof(FlowGemm), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(h->flow_tmaps.p, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaStreamSynchronize(st));   // `maps` / `gemms` are stack objects
+  fp.gemms = static_cast<const FlowGemm*>(h->flow_gemms.p);
+  fp.tmaps = static_cast<const CUtensorMap*>(h->flow_tmaps.p);
+  return 0;
+}
+
+static int flow_smem_bytes(const FlowParams& fp) {
+  return 1024 + fp.nw * FLOW_W_BYTES + fp.na * fp.a_slot_bytes + 2 * FLOW_STG_BYTES + FLOW_BAR_BYTES;
+}
+
+template <int NV>
+static int launch_flow_nv(FmtHandle* h, cudaStream_t st, bool probe_only) {
+  const int smem = flow_smem_bytes(h->flow_params);
+  CUDA_OK(cudaFuncSetAttribute(fmt_flow_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int occ = 0;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fmt_flow_kernel<NV>, FLOW_THREADS, smem));
+  REQUIRE(occ >= 1, "flow kernel does not fit on an SM (%d B smem)", smem);
+  if (probe_only) return 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(h->num_sms); cfg.blockDim = dim3(FLOW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: they wait for one another's counters
+  attrs[0].val.cooperative = 1;
+  cfg.attrs = attrs; cfg.numAttrs = 1;
+  CUDA_OK(cudaLaunchKernelEx(&cfg, fmt_flow_kernel<NV>, h->flow_params));
+  count_launch(h);
+  return 0;
+}
+
+static int launch_flow(FmtHandle* h, cudaStream_t st, bool probe_only = false) {
+  if (!probe_only) {
+    CUDA_OK(cudaMemsetAsync(h->flow_acc.p, 0, h->flow_acc.bytes, st));
+    CUDA_OK(cudaMemsetAsync(h->flow_flags.p, 0, h->flow_flags.bytes, st));
+  }
+  switch (h->shape.H / 128) {
+    case 1: return launch_flow_nv<1>(h, st, probe_only);
+    case 2: return launch_flow_nv<2>(h, st, probe_only);
+    case 4: return launch_flow_nv<4>(h, st, probe_only);
+    case 8: return launch_flow_nv<8>(h, st, probe_only);
+  }
+  return set_err(-1, "flow kernel: dim_h %d unsupported", h->shape.H);
+}
+
 // The whole window: prepare -> tables -> S steps x stages -> finalize.  This is what gets captured in the graph.
 template <typename T>
 static int enqueue_window(FmtHandle* h, cudaStream_t st) {
@@ -602,9 +777,10 @@ static int enqueue_window(FmtHandle* h, cudaStream_t st) {
                 static_cast<float*>(h->prevx.p), ax));
   if (S > 0) FMT_OK(enqueue_prepare<T>(h, st));
   if (h->window_active && S > 0) {
-    // small-R plan: every evaluation of the window runs inside ONE persistent kernel (window.cuh)
+    // small-R plan: every evaluation of the window runs inside ONE persistent kernel (flow.cuh; window.cuh with FMT_WINDOW=1/2)
     FMT_OK(enqueue_tables<T>(h, 0, h->n_eval, st));
-    FMT_OK(launch_window(h, st));
+    if (h->flow_active) FMT_OK(launch_flow(h, st));
+    else FMT_OK(launch_window(h, st));
     FMT_OK(launch(h, finalize_window_kernel, gx, blk, 0, st, 1, wa, s, static_cast<const float*>(x_state), static_cast<float*>(h->prevx.p)));
     return 0;
   }
@@ -721,6 +897,10 @@ int32_t fmt_create(const FmtDims* dims, const void* const* wp, int32_t n_ptrs, i
   h->NT = d.depth * 6 * d.dim_h + 2 * d.dim_h;
   if (const char* e = getenv("FMT_PDL")) h->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("FMT_WINDOW")) h->use_window = atoi(e);
+  if (const char* e = getenv("FMT_FLOW_CH")) { const int v = atoi(e); if (v == 32 || v == 64) h->flow_ch = v; }
+  if (const char* e = getenv("FMT_FLOW_MAX_ROWS")) h->flow_max_rows = atoi(e);
+  if (const char* e = getenv("FMT_FLOW_GELU_F4")) h->flow_gelu_f4 = atoi(e);
+  if (const char* e = getenv("FMT_FLOW_SPIN_MS")) h->flow_spin_limit = static_cast<long long>(atof(e) * 1.9e6);
   if (const char* e = getenv("FMT_WIN_SPG")) h->win_spg = atoi(e);
   if (const char* e = getenv("FMT_WIN_FUSE_GELU")) h->win_fuse_gelu = atoi(e) != 0;
   if (const char* e = getenv("FMT_WIN_NF")) sscanf(e, "%d,%d,%d,%d", &h->win_nf[0], &h->win_nf[1], &h->win_nf[2], &h->win_nf[3]);
@@ -802,7 +982,8 @@ int32_t fmt_destroy(FmtHandle* h) {
   for (void* p : h->owned) cudaFree(p);
   DevBuf* bufs[] = {&h->cond, &h->cemb, &h->temb, &h->tfreq, &h->th, &h->silu, &h->table, &h->xstate, &h->ystage, &h->kbuf, &h->prevx, &h->ax,
                     &h->X, &h->A1, &h->QKV, &h->A2, &h->Hm, &h->V, &h->ddt, &h->dteval, &h->wargs, &h->st_rs, &h->st_wa, &h->st_we, &h->st_noise, &h->st_rd,
-                    &h->win_params, &h->win_tmaps, &h->win_acc, &h->win_bar, &h->win_trace, &h->win_act};
+                    &h->win_params, &h->win_tmaps, &h->win_acc, &h->win_bar, &h->win_trace, &h->win_act,
+                    &h->flow_gemms, &h->flow_tmaps, &h->flow_acc, &h->flow_act, &h->flow_flags, &h->flow_trace};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->win_err_host) cudaFreeHost(h->win_err_host);
@@ -820,6 +1001,13 @@ int64_t fmt_launch_count(const FmtHandle* hc, int32_t reset) {
 }
 int32_t fmt_graph_kernel_nodes(const FmtHandle* h) { return h ? h->graph_nodes : 0; }
 int64_t fmt_debug_window_trace(const FmtHandle* h, int64_t* out, int64_t max_elems) {
+  if (h && h->flow_active && h->flow_trace.p) {   // dataflow kernel: [cta][engine][stage][chunk][4] SM-clock stamps
+    const int64_t nf = static_cast<int64_t>(h->flow_trace.bytes / sizeof(long long));
+    if (out != nullptr && max_elems >= nf) {
+      if (cudaMemcpy(out, h->flow_trace.p, nf * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    }
+    return nf;
+  }
   if (!h || !h->win_trace.p) return 0;
   const int64_t n = static_cast<int64_t>(h->num_sms) * h->win_trace_stride * 6;
   if (out != nullptr && max_elems >= n) {
@@ -924,8 +1112,14 @@ int32_t fmt_configure(FmtHandle* h, const FmtPlan* p, void* stream) {
     CUDA_OK(cudaStreamSynchronize(st));   // t_eval/dt host vectors may be reassigned by the next configure
   }
 
-  h->window_active = window_eligible(h, p) && h->table_chunk == ne;
-  if (h->window_active) {
+  // dataflow kernel first (FMT_WINDOW=3, the default); its setup fails soft: the plan then runs one kernel per op
+  h->flow_active = false;
+  if (flow_eligible(h, p) && h->table_chunk == ne) {
+    if (setup_flow(h, st) == 0 && launch_flow(h, st, /*probe_only=*/true) == 0) h->flow_active = true;
+    else (void)cudaGetLastError();
+  }
+  h->window_active = h->flow_active || (window_eligible(h, p) && h->table_chunk == ne);
+  if (h->window_active && !h->flow_active) {
     // the persistent kernel synchronises across the grid: it needs one resident CTA on every SM, else the plan runs one kernel per op
     int occ = 0;
     cudaError_t oe = cudaErrorUnknown;
@@ -941,7 +1135,7 @@ int32_t fmt_configure(FmtHandle* h, const FmtPlan* p, void* stream) {
     }
     if (oe != cudaSuccess || occ < 1) { (void)cudaGetLastError(); h->window_active = false; }
   }
-  if (h->window_active) FMT_OK(setup_window(h, st));
+  if (h->window_active && !h->flow_active) FMT_OK(setup_window(h, st));
 
   // capture one window as a CUDA graph
   {
