@@ -330,14 +330,17 @@ __device__ __forceinline__ int flow_stid() { return static_cast<int>(threadIdx.x
 // NOT depend on the GEMM (AdaLN table rows from HBM, residual, biases) first and only then calls flow_simt_wait, so that their
 // latency hides behind the wait.
 struct FlowWait {
-  const unsigned* f[4];
+  const unsigned* f0;      // counter of the chunk itself
+  int stride1, stride2, n; // counter i >= 1 of n sits at f0 + stride1 + (i - 1) * stride2  (no pointer array: no local memory)
   unsigned need;
-  int n, code;
+  int code;
   int e, si, c;
 };
 __device__ __forceinline__ void flow_simt_wait(const FlowParams& p, const FlowWait& w) {
   if (flow_stid() == 0) {
-    for (int i = 0; i < w.n; ++i) flow_wait_flag(p, w.f[i], w.need, w.code);
+    flow_wait_flag(p, w.f0, w.need, w.code);
+    if (w.n > 1) flow_wait_flag(p, w.f0 + w.stride1, w.need, w.code);
+    for (int i = 2; i < w.n; ++i) flow_wait_flag(p, w.f0 + w.stride1 + (i - 1) * w.stride2, w.need, w.code);
     flow_mark(p, w.e, 1, w.si, w.c, 1);
   }
   named_bar_sync(1, FLOW_SIMT);
@@ -370,18 +373,17 @@ __device__ __forceinline__ void flow_row_units(const FlowParams& p, const FlowCh
     const __nv_bfloat16* trow = table_e + static_cast<size_t>(ck.rr0 + (valid ? r : 0)) * p.NT + c0;
     float4 a[FPL], x[FPL], b[FPL], ps[FPL];
     uint2 tg[FPL], tsh[FPL], tsc[FPL];
-    if (valid) {
+    // unconditional (row 0 stands in for a row past the chunk): conditionally defined registers would be demoted to local memory
 #pragma unroll
-      for (int i = 0; i < FPL; ++i) {
-        tsh[i] = ld_nc_u2(trow + shift_off + i * 128);
-        tsc[i] = ld_nc_u2(trow + scale_off + i * 128);
-        b[i] = __ldg(reinterpret_cast<const float4*>(bias + c0 + i * 128));
-        if (mode == 1) {
-          x[i] = ldcg4(xr + i * 128);
-          tg[i] = ld_nc_u2(trow + gate_off + i * 128);
-        } else {
-          ps[i] = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(ck.f0 + r) * H + c0 + i * 128));
-        }
+    for (int i = 0; i < FPL; ++i) {
+      tsh[i] = ld_nc_u2(trow + shift_off + i * 128);
+      tsc[i] = ld_nc_u2(trow + scale_off + i * 128);
+      b[i] = __ldg(reinterpret_cast<const float4*>(bias + c0 + i * 128));
+      if (mode == 1) {
+        x[i] = ldcg4(xr + i * 128);
+        tg[i] = ld_nc_u2(trow + gate_off + i * 128);
+      } else {
+        ps[i] = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(ck.f0 + (valid ? r : 0)) * H + c0 + i * 128));
       }
     }
     if (!waited) { flow_simt_wait(p, w); waited = true; }
@@ -449,108 +451,152 @@ __device__ __forceinline__ void flow_row_units(const FlowParams& p, const FlowCh
   if (!waited) flow_simt_wait(p, w);
 }
 
-// ATTN units: 8 tasks per unit, one per warp; a task = (two consecutive rows, one head): band-masked attention (FMT.py:15-19,
-// 69-88) straight from the fp32 QKV accumulator of this block's parity (+ qkv bias).  The two rows share all but two of their
-// keys, so every k / v row is fetched once for both.  Keys / values of the neighbouring chunk of the same sequence are read
-// across the chunk boundary.  Also zeroes the task's slices in the OTHER parity buffer (read for the last time one block ago).
-template <int VPL>
+// ATTN units: a unit = (one head, one group of consecutive row pairs of the chunk); inside it a warp takes a row pair, one row per
+// half warp, DPL = head_dim / 16 dimensions per lane: band-masked attention (FMT.py:15-19,69-88) straight from the fp32 QKV
+// accumulator of this block's parity (+ qkv bias).
+//   * A CTA's L2 -> SM path moves ~32 B per clock, so what a CTA fetches decides the stage: consecutive rows of ONE head share all
+//     but a halo of their keys, and the q / k / v loads are ordinary cached loads - the acquire poll in front of them invalidated the
+//     L1, the first warp to touch a line fetches it, the other warps of the CTA hit (or merge with the miss).  A unit of 10 rows reads
+//     (10 + 14 + 14) x 512 B instead of 10 x 11 x 512 B.
+//   * Everything after the loads is a dependent chain executed by ONE warp, so it is laid out for few instructions: dot products
+//     reduce over 16 lanes (4 shuffle rounds serve both rows), the softmax over a batch of keys is the plain two-pass form (max, then
+//     independent exponentials) and batches are merged online only when the band is wider than KB keys.
+// Keys / values of the neighbouring chunk of the same sequence are read across the chunk boundary.  Also zeroes the rows' slices in the
+// OTHER parity buffer (read for the last time one block ago).
+template <int VL> struct F32VecCa;
+template <> struct F32VecCa<2> { static __device__ __forceinline__ void ld(const float* p, float (&v)[2]) { float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; } };
+template <> struct F32VecCa<4> { static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) { float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; } };
+template <int DPL>
 __device__ __forceinline__ void flow_attn_units(const FlowParams& p, const FlowChunk& ck, int c, const FlowUnits& un, const float* __restrict__ qkv,
                                                 float* __restrict__ qkv_other, const float* __restrict__ bqkv, const FlowWait& w) {
   const int lane = threadIdx.x & 31, mw = (threadIdx.x >> 5) - FLOW_SIMT_WARP0;
-  constexpr int hd = VPL * 32;
+  constexpr int hd = DPL * 16;
+  constexpr int VL = DPL >= 4 ? 4 : DPL, NVL = DPL / VL;        // vector loads of VL floats, NVL per row
+  const int half = lane >> 4, sl = lane & 15;
   const int N = p.s.N, heads = p.heads, H = p.s.H, ld = 3 * H, win = p.window;
   const float scale = rsqrtf(static_cast<float>(hd));
   const size_t seq_row0 = static_cast<size_t>(ck.seq) * p.NPs;
-  const int n_tasks = ((ck.vr + 1) >> 1) * heads;
-  flow_simt_wait(p, w);
-  for (int u = un.u0; u < un.n_units; u += un.stride) {
-    const int task = u * 8 + mw;
-    if (task >= n_tasks) continue;
-    const int rp = task / heads, hh = task - rp * heads;       // one division per stage per warp (off the flag path)
-    const int r0 = 2 * rp;
-    const bool has1 = r0 + 1 < ck.vr;
-    const int fi0 = ck.f0 + r0, fi1 = fi0 + 1;
-    const float* base = qkv + seq_row0 * ld + hh * hd + lane * VPL;
-    const float* bq = bqkv + hh * hd + lane * VPL;
-    const int j0 = max(0, fi0 - win), j1 = min(N - 1, (has1 ? fi1 : fi0) + win);
-    float q0[VPL], q1[VPL], bk[VPL];
-    F32Vec<VPL>::ld(base + static_cast<size_t>(fi0) * ld, q0);
-    F32Vec<VPL>::ld(base + static_cast<size_t>(has1 ? fi1 : fi0) * ld, q1);
-    float mx0 = -INFINITY, mx1 = -INFINITY, den0 = 0.f, den1 = 0.f, acc0[VPL], acc1[VPL];
+  const int n_rp = (ck.vr + 1) >> 1;                             // row pairs of the chunk
+  const int n_grp = un.n_units / heads;                          // groups of row pairs per head
+  const int ppg = (n_rp + n_grp - 1) / n_grp;                    // row pairs per group
+  // the biases of the first unit's head do not depend on the GEMM: fetched before the wait (the poll invalidates the L1 under them)
+  float bqv[DPL], bk[DPL], bv[DPL];
+  int hb = (un.u0 >= 0 ? un.u0 : 0) % heads;
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
-    constexpr int KB = 6;
+  for (int k = 0; k < DPL; ++k) {
+    const float* bq = bqkv + hb * hd + sl * DPL;
+    bqv[k] = __ldg(bq + k); bk[k] = __ldg(bq + H + k); bv[k] = __ldg(bq + 2 * H + k);
+  }
+  flow_simt_wait(p, w);
+  for (int u = un.u0; u < un.n_units; u += un.stride)
+  for (int pp = mw; pp < ppg; pp += 8) {
+    const int g = u / heads, hh = u - g * heads;                 // one division per stage per warp (off the flag path)
+    const int rp = g * ppg + pp;
+    if (rp >= n_rp) continue;
+    if (hh != hb) {                                              // a CTA with several units (more chunks than CTAs per head): reload
+      hb = hh;
+#pragma unroll
+      for (int k = 0; k < DPL; ++k) {
+        const float* bq = bqkv + hb * hd + sl * DPL;
+        bqv[k] = __ldg(bq + k); bk[k] = __ldg(bq + H + k); bv[k] = __ldg(bq + 2 * H + k);
+      }
+    }
+    const bool valid = 2 * rp + half < ck.vr;
+    const int r = valid ? 2 * rp + half : 2 * rp;              // an odd last row: the upper half warp shadows the lower one and stores nothing
+    const int fi = ck.f0 + r;
+    const float* base = qkv + seq_row0 * ld + hh * hd + sl * DPL;
+    const int j0 = max(0, fi - win), j1 = min(N - 1, fi + win);
+    const int n_keys = max(j1 - j0, __shfl_xor_sync(0xffffffffu, j1 - j0, 16)) + 1;    // warp-uniform trip count
+    float q[DPL], acc[DPL];
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) F32VecCa<VL>::ld(base + static_cast<size_t>(fi) * ld + i * VL, *reinterpret_cast<float(*)[VL]>(&q[i * VL]));
+    float mx = -INFINITY, den = 0.f;
+#pragma unroll
+    for (int k = 0; k < DPL; ++k) acc[k] = 0.f;
+    constexpr int KB = 5;
     bool first = true;
 #pragma unroll 1
-    for (int jb = j0; jb <= j1; jb += KB) {
-      float kv[KB][VPL], vv[KB][VPL], s0[KB], s1[KB];
+    for (int jb = 0; jb < n_keys; jb += KB) {
+      float kv[KB][DPL], vv[KB][DPL], sc[KB];
 #pragma unroll
       for (int t = 0; t < KB; ++t) {
-        const int j = min(jb + t, j1);
-        F32Vec<VPL>::ld(base + static_cast<size_t>(j) * ld + H, kv[t]);
-        F32Vec<VPL>::ld(base + static_cast<size_t>(j) * ld + 2 * H, vv[t]);
+        const int j = min(j0 + jb + t, j1);
+#pragma unroll
+        for (int i = 0; i < NVL; ++i) {
+          F32VecCa<VL>::ld(base + static_cast<size_t>(j) * ld + H + i * VL, *reinterpret_cast<float(*)[VL]>(&kv[t][i * VL]));
+          F32VecCa<VL>::ld(base + static_cast<size_t>(j) * ld + 2 * H + i * VL, *reinterpret_cast<float(*)[VL]>(&vv[t][i * VL]));
+        }
       }
       if (first) {
 #pragma unroll
-        for (int k = 0; k < VPL; ++k) { const float b = __ldg(bq + k); q0[k] += b; q1[k] += b; bk[k] = __ldg(bq + H + k); }
+        for (int k = 0; k < DPL; ++k) q[k] = (q[k] + bqv[k]) * scale;
         first = false;
       }
 #pragma unroll
       for (int t = 0; t < KB; ++t) {
-        float d0 = 0.f, d1 = 0.f;
+        float d = 0.f;
 #pragma unroll
-        for (int k = 0; k < VPL; ++k) { const float kk = kv[t][k] + bk[k]; d0 = fmaf(q0[k], kk, d0); d1 = fmaf(q1[k], kk, d1); }
-        s0[t] = d0; s1[t] = d1;
+        for (int k = 0; k < DPL; ++k) d = fmaf(q[k], kv[t][k] + bk[k], d);
+        sc[t] = d;
       }
+      if (flow_stid() == 0) flow_mark(p, w.e, 1, w.si, w.c, 5);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
+      for (int o = 8; o > 0; o >>= 1)
 #pragma unroll
-        for (int t = 0; t < KB; ++t) { s0[t] += __shfl_xor_sync(0xffffffffu, s0[t], o); s1[t] += __shfl_xor_sync(0xffffffffu, s1[t], o); }
+        for (int t = 0; t < KB; ++t) sc[t] += __shfl_xor_sync(0xffffffffu, sc[t], o);
+      if (flow_stid() == 0) flow_mark(p, w.e, 1, w.si, w.c, 6);
+      float bm = -INFINITY;
 #pragma unroll
       for (int t = 0; t < KB; ++t) {
-        const int j = jb + t;
-        if (j <= j1) {
-          if (j >= fi0 - win && j <= fi0 + win) {
-            const float sc = s0[t] * scale, nmx = fmaxf(mx0, sc);
-            const float corr = __expf(mx0 - nmx), pr = __expf(sc - nmx);
-            den0 = den0 * corr + pr;
-#pragma unroll
-            for (int k = 0; k < VPL; ++k) acc0[k] = fmaf(acc0[k], corr, pr * vv[t][k]);
-            mx0 = nmx;
-          }
-          if (has1 && j >= fi1 - win && j <= fi1 + win) {
-            const float sc = s1[t] * scale, nmx = fmaxf(mx1, sc);
-            const float corr = __expf(mx1 - nmx), pr = __expf(sc - nmx);
-            den1 = den1 * corr + pr;
-#pragma unroll
-            for (int k = 0; k < VPL; ++k) acc1[k] = fmaf(acc1[k], corr, pr * vv[t][k]);
-            mx1 = nmx;
-          }
-        }
+        if (j0 + jb + t > j1) sc[t] = -INFINITY;
+        bm = fmaxf(bm, sc[t]);
       }
-    }
-    const float inv0 = __fdividef(1.f, den0), inv1 = has1 ? __fdividef(1.f, den1) : 0.f;
-    float o0[VPL], o1[VPL];
+      const float nmx = fmaxf(mx, bm);                           // finite: the first batch of a row always holds a valid key
+      const float corr = __expf(mx - nmx);
+      float ps = 0.f, pr[KB];
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) {                              // sum_c p_c (v_c + b) / den = sum_c p_c v_c / den + b
-      const float bv = __ldg(bq + 2 * H + k);
-      o0[k] = fmaf(acc0[k], inv0, bv); o1[k] = fmaf(acc1[k], inv1, bv);
-    }
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int t = 0; t < KB; ++t) { pr[t] = __expf(sc[t] - nmx); ps += pr[t]; }
+      den = fmaf(den, corr, ps);
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      if (rr == 1 && !has1) break;
-      // VPL <= 4 elements stay inside one 16-byte chunk of the swizzled operand tile
-      __nv_bfloat16* op = p.A2 + flow_tiled_off(c, r0 + rr, hh * hd + lane * VPL, H >> 6, p.CH);
+      for (int k = 0; k < DPL; ++k) {
+        float a = acc[k] * corr;
+#pragma unroll
+        for (int t = 0; t < KB; ++t) a = fmaf(pr[t], vv[t][k], a);
+        acc[k] = a;
+      }
+      mx = nmx;
+    }
+    if (flow_stid() == 0) flow_mark(p, w.e, 1, w.si, w.c, 7);
+    const float inv = __fdividef(1.f, den);
+    float o[DPL];
+#pragma unroll
+    for (int k = 0; k < DPL; ++k) o[k] = fmaf(acc[k], inv, bv[k]);   // sum_c p_c (v_c + b) / den = sum_c p_c v_c / den + b
+    if (valid) {
+      // DPL <= 8 elements stay inside one 16-byte chunk of the swizzled operand tile
+      __nv_bfloat16* op = p.A2 + flow_tiled_off(c, r, hh * hd + sl * DPL, H >> 6, p.CH);
       // q / k / v slices of (row, head) in the other parity buffer: every reader (this chunk's and the neighbours' previous ATTN
       // stage) finished before this block's qkv GEMM could complete
-      float* z = qkv_other + (seq_row0 + fi0 + rr) * ld + hh * hd + lane * VPL;
-      if constexpr (VPL == 4) {
-        *reinterpret_cast<uint2*>(op) = f32x4_to_bf16(rr == 0 ? o0 : o1);
-        *reinterpret_cast<float4*>(z) = zero4; *reinterpret_cast<float4*>(z + H) = zero4; *reinterpret_cast<float4*>(z + 2 * H) = zero4;
+      float* z = qkv_other + (seq_row0 + fi) * ld + hh * hd + sl * DPL;
+      if constexpr (DPL == 8) {
+        uint4 t;
+        const uint2 lo = f32x4_to_bf16(*reinterpret_cast<const float(*)[4]>(&o[0])), hi = f32x4_to_bf16(*reinterpret_cast<const float(*)[4]>(&o[4]));
+        t.x = lo.x; t.y = lo.y; t.z = hi.x; t.w = hi.y;
+        *reinterpret_cast<uint4*>(op) = t;
+      } else if constexpr (DPL == 4) {
+        *reinterpret_cast<uint2*>(op) = f32x4_to_bf16(*reinterpret_cast<const float(*)[4]>(&o[0]));
       } else {
 #pragma unroll
-        for (int k = 0; k < VPL; ++k) { op[k] = __float2bfloat16_rn(rr == 0 ? o0[k] : o1[k]); z[k] = 0.f; z[H + k] = 0.f; z[2 * H + k] = 0.f; }
+        for (int k = 0; k < DPL; ++k) op[k] = __float2bfloat16_rn(o[k]);
+      }
+      if constexpr (DPL >= 4) {
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < DPL / 4; ++i) {
+          *reinterpret_cast<float4*>(z + i * 4) = zero4; *reinterpret_cast<float4*>(z + H + i * 4) = zero4; *reinterpret_cast<float4*>(z + 2 * H + i * 4) = zero4;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) { z[k] = 0.f; z[H + k] = 0.f; z[2 * H + k] = 0.f; }
       }
     }
   }
@@ -565,28 +611,32 @@ __device__ __forceinline__ void flow_gelu_units(const FlowParams& p, const FlowC
   float* hacc = p.Hacc + static_cast<size_t>(ck.rp0) * M4;
   constexpr int NB = 5;
   const int stid = flow_stid();
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   flow_simt_wait(p, w);
 #pragma unroll 1
   for (int u = un.u0; u < un.n_units; u += NB * un.stride) {
     float4 a[NB], b[NB];
-    int row[NB], col[NB];
-#pragma unroll
-    for (int k = 0; k < NB; ++k) {
+    // slab sl -> (row, first column of this thread); recomputed for the stores instead of being kept in registers
+    auto locate = [&](int k, int& row, int& col) -> bool {
       const int sl = u + k * un.stride;
-      row[k] = sl / n_q;
-      col[k] = ((sl - row[k] * n_q) * FLOW_SIMT + stid) * 4;
-      if (sl >= un.n_units || col[k] >= M4) row[k] = -1;
-      if (row[k] >= 0) {
-        a[k] = ldcg4(hacc + static_cast<size_t>(row[k]) * M4 + col[k]);
-        b[k] = __ldg(reinterpret_cast<const float4*>(b1 + col[k]));
-      }
+      row = sl / n_q;
+      col = ((sl - row * n_q) * FLOW_SIMT + stid) * 4;
+      return sl < un.n_units && col < M4;
+    };
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {                  // unconditional loads (a clamped address when the slab is out of range): conditionally
+      int row, col;                                 // defined registers would be demoted to local memory
+      if (!locate(k, row, col)) { row = 0; col = 0; }
+      a[k] = ldcg4(hacc + static_cast<size_t>(row) * M4 + col);
+      b[k] = __ldg(reinterpret_cast<const float4*>(b1 + col));
     }
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
-      if (row[k] >= 0) {
+      int row, col;
+      if (locate(k, row, col)) {
         float v[4] = {gelu_tanh_fast(a[k].x + b[k].x), gelu_tanh_fast(a[k].y + b[k].y), gelu_tanh_fast(a[k].z + b[k].z), gelu_tanh_fast(a[k].w + b[k].w)};
-        *reinterpret_cast<uint2*>(p.Hm + flow_tiled_off(c, row[k], col[k], nkb, p.CH)) = f32x4_to_bf16(v);
-        *reinterpret_cast<float4*>(hacc + static_cast<size_t>(row[k]) * M4 + col[k]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<uint2*>(p.Hm + flow_tiled_off(c, row, col, nkb, p.CH)) = f32x4_to_bf16(v);
+        *reinterpret_cast<float4*>(hacc + static_cast<size_t>(row) * M4 + col) = zero4;
       }
     }
   }
@@ -606,14 +656,11 @@ __device__ __forceinline__ void flow_comb_unit(const FlowParams& p, const FlowCh
   const int b = ck.clip;
   const size_t nx = static_cast<size_t>(s.B) * s.L * s.W;
   const size_t o = (static_cast<size_t>(b) * s.L + (f - s.P)) * s.W + j;
-  float vb[4] = {0.f, 0.f, 0.f, 0.f};
-  float* va[4];
+  float vb[4];
+  float* const va0 = p.Vacc + (static_cast<size_t>(b) * p.NPs + f) * s.W + j;          // branch br: + br * vstride
+  const size_t vstride = static_cast<size_t>(s.B) * p.NPs * s.W;
 #pragma unroll
-  for (int br = 0; br < 4; ++br)
-    if (br < s.nb) {
-      va[br] = p.Vacc + (static_cast<size_t>(br * s.B + b) * p.NPs + f) * s.W + j;
-      vb[br] = __ldcg(va[br]);
-    }
+  for (int br = 0; br < 4; ++br) vb[br] = __ldcg(va0 + (br < s.nb ? br : 0) * vstride);
   const float bd = __ldg(p.b_dec + j);
   const float dt = __ldg(p.ddt + step);
   const float a_s = __ldg(&p.wargs->a_scale), r_s = __ldg(&p.wargs->r_scale), e_s = __ldg(&p.wargs->e_scale);
@@ -626,7 +673,7 @@ __device__ __forceinline__ void flow_comb_unit(const FlowParams& p, const FlowCh
   }
 #pragma unroll
   for (int br = 0; br < 4; ++br)
-    if (br < s.nb) { vb[br] += bd; *va[br] = 0.f; }
+    if (br < s.nb) { vb[br] += bd; va0[br * vstride] = 0.f; }
   float v;
   if (s.nb == 1) v = vb[0];
   else if (s.nb == 3) v = vb[0] + a_s * (vb[2] - vb[0]) + e_s * (vb[1] - vb[2]);
@@ -672,15 +719,17 @@ __device__ __forceinline__ void flow_simt_engine(const FlowParams& p, const Flow
         FlowWait w;
         w.need = static_cast<unsigned>(items[si].n_items);
         w.code = 0x08000000 | (e << 16) | (si << 8) | c;
-        w.e = e; w.si = si; w.c = c; w.n = 0;
-        if (kind == FK_COMB) {
-          for (int br = 0; br < p.s.nb; ++br) w.f[w.n++] = flow_flag(p.g_done, p, e, si, c + br * p.s.B * p.nsub);
-        } else {
-          w.f[w.n++] = flow_flag(p.g_done, p, e, si, c);
-          if (kind == FK_ATTN) {                                            // the band crosses into the neighbouring chunks of the sequence
-            if (ck.sub > 0) w.f[w.n++] = flow_flag(p.g_done, p, e, si, c - 1);
-            if (ck.sub < p.nsub - 1) w.f[w.n++] = flow_flag(p.g_done, p, e, si, c + 1);
-          }
+        w.e = e; w.si = si; w.c = c; w.n = 1;
+        w.f0 = flow_flag(p.g_done, p, e, si, c);
+        w.stride1 = w.stride2 = 0;
+        if (kind == FK_COMB) {                                              // the same (clip, sub-chunk) of every branch
+          w.n = p.s.nb;
+          w.stride1 = w.stride2 = p.s.B * p.nsub * FLOW_FLAG_STRIDE;
+        } else if (kind == FK_ATTN) {                                       // the band crosses into the neighbouring chunks of the sequence
+          const bool lo = ck.sub > 0, hi = ck.sub < p.nsub - 1;
+          if (lo && hi) { w.n = 3; w.stride1 = -FLOW_FLAG_STRIDE; w.stride2 = 2 * FLOW_FLAG_STRIDE; }
+          else if (lo) { w.n = 2; w.stride1 = -FLOW_FLAG_STRIDE; }
+          else if (hi) { w.n = 2; w.stride1 = FLOW_FLAG_STRIDE; }
         }
         if (stid == 0) flow_mark(p, e, 1, si, c, 0);
         // ---- this CTA's units of (stage, chunk)
@@ -700,9 +749,9 @@ __device__ __forceinline__ void flow_simt_engine(const FlowParams& p, const Flow
           const int par = (e * D + blk) & 1;
           const float* q = p.QKVacc + par * qkv_buf;
           float* qo = p.QKVacc + (par ^ 1) * qkv_buf;
-          if (hd == 128) flow_attn_units<4>(p, ck, c, un, q, qo, p.b_qkv[blk], w);
-          else if (hd == 64) flow_attn_units<2>(p, ck, c, un, q, qo, p.b_qkv[blk], w);
-          else flow_attn_units<1>(p, ck, c, un, q, qo, p.b_qkv[blk], w);
+          if (hd == 128) flow_attn_units<8>(p, ck, c, un, q, qo, p.b_qkv[blk], w);
+          else if (hd == 64) flow_attn_units<4>(p, ck, c, un, q, qo, p.b_qkv[blk], w);
+          else flow_attn_units<2>(p, ck, c, un, q, qo, p.b_qkv[blk], w);
         } else if (kind == FK_GELU) {
           flow_gelu_units(p, ck, c, un, p.b_fc1[blk], w);
         } else {
@@ -776,7 +825,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) fmt_flow_kernel(const __grid_
       int n_units;
       const int row_wpr = NV >= 4 ? 4 : NV;                                  // as in flow_row_units
       if (kind == FK_ROW) n_units = (ck.vr + 8 / row_wpr - 1) / (8 / row_wpr);
-      else if (kind == FK_ATTN) n_units = (((ck.vr + 1) >> 1) * p.heads + 7) / 8;
+      else if (kind == FK_ATTN) n_units = p.heads * max(1, (nctas / p.n_chunks) / p.heads);   // (head, group of row pairs), see flow_attn_units
       else if (kind == FK_GELU) n_units = ck.vr * ((p.mlp_hidden / 4 + FLOW_SIMT - 1) / FLOW_SIMT);
       else n_units = ck.seq < p.s.B ? (max(0, ck.f0 + ck.vr - max(ck.f0, p.s.P)) * p.s.W + FLOW_SIMT - 1) / FLOW_SIMT : 0;   // published on branch 0's chunks
       // The row-wise stages of a chunk run on that chunk's own slice of the grid, so that the in-order SIMT engine of a CTA
@@ -814,7 +863,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) fmt_flow_kernel(const __grid_
   const int n_eval = p.n_steps * p.n_stages;
   if (p.trace != nullptr && threadIdx.x == 96) flow_calibrate(p, 0);     // idle warp 3: SM clock <-> global timer
 
-  // register budget per warpgroup (64 K registers per SM): 64 + 96 + 2 x 176 = 512 per lane quartet
+  // register budget per warpgroup (64 K registers per SM): 64 + 80 + 2 x 184 = 512 per lane quartet
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 0) {
@@ -827,10 +876,10 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) fmt_flow_kernel(const __grid_
       flow_mma_issuer(p, items, sm, tmem_base, n_eval);
     }
   } else if (warp < 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     flow_epilogue(p, items, chunks, sm, tmem_base, n_eval);
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
     flow_simt_engine<NV>(p, items, chunks, units, red_smem, n_eval);
   }
   tc_fence_before();

@@ -206,9 +206,11 @@ def test_window_kernel_matches_per_op_path(pkg, monkeypatch, method, nfe, nb_sca
     g = torch.Generator().manual_seed(5)
     noise = torch.stack([torch.randn(B, d.frames_per_clip, d.dim_w, generator=g) for _ in range(3)]).to(DEV)
     outs = {}
+    # "3": dataflow window kernel (flow.cuh, the default), "3c": the same with 32-row chunks (attention crosses chunk boundaries);
     # "2": grouped window kernel (one slice of the SMs per sequence, GELU fused into fc1's epilogue); "2s": same with the
-    # separate GELU stage and a 2-way K split of fc1; "1": split-K window kernel; "0": one kernel per op
-    for flag in ("2", "2s", "1", "0"):
+    # separate GELU stage and a 2-way K split of fc1; "1": barrier-stepped split-K window kernel; "0": one kernel per op
+    for flag in ("3", "3c", "2", "2s", "1", "0"):
+        monkeypatch.setenv("FMT_FLOW_CH", "32" if flag == "3c" else "64")
         monkeypatch.setenv("FMT_WINDOW", flag[0])
         monkeypatch.setenv("FMT_WIN_FUSE_GELU", "0" if flag == "2s" else "1")
         monkeypatch.setenv("FMT_WIN_PK", "0,0,2,0" if flag == "2s" else "0,0,0,0")
@@ -219,7 +221,7 @@ def test_window_kernel_matches_per_op_path(pkg, monkeypatch, method, nfe, nb_sca
         torch.cuda.synchronize()
         assert be.window_kernel_status() == (0 if flag != "0" else -1)
         be.close()
-    for flag in ("2", "2s", "1"):
+    for flag in ("3", "3c", "2", "2s", "1"):
         assert torch.isfinite(outs[flag]).all(), flag
         assert cases.max_abs(outs[flag], outs["0"]) <= 1e-2, (flag, cases.max_abs(outs[flag], outs["0"]))
 
@@ -256,7 +258,7 @@ def _oracle_on_gpu(d, r_s, wa, we, T, noise, **kw):
         return O.sample_loop(Wd, d, r_s.to(DEV), wa.to(DEV), we.to(DEV), T, noise=noise.to(DEV), **kw).cpu()
 
 
-@pytest.mark.parametrize("window_flag", ["1", "2", "0"])
+@pytest.mark.parametrize("window_flag", ["3", "1", "2", "0"])
 def test_non_default_window_geometry(pkg, monkeypatch, window_flag):
     """loader widgets other than the defaults (nodes_vadv_loader.py:684-704) - attention_window 4 (the
     general band-attention code, not the 5-key fast path), 6 context frames, 1.6 s windows (L = 40) - on the full-width

@@ -94,6 +94,9 @@ with np.errstate(all="ignore"):
         K = S[:, sl]
         print(f"  {kind:5s}: wait {np.nanmean(K[..., 1] - K[..., 0]):5.2f} work {np.nanmean(K[..., 2] - K[..., 1]):5.2f} fence {np.nanmean(K[..., 3] - K[..., 2]):5.2f} "
               f"release {np.nanmean(K[..., 4] - K[..., 3]):5.2f}  (stage, chunk) pairs per CTA and stage: {np.mean(np.sum(~np.isnan(K[..., 1]), axis=2)):.2f}")
+    A = S[:, 0::4]
+    print("  attn detail (thread 0 of the SIMT engine): ok -> scores computed (loads landed) %.2f | shuffles %.2f | softmax %.2f | outputs + stores %.2f" % (
+        np.nanmean(A[..., 5] - A[..., 1]), np.nanmean(A[..., 6] - A[..., 5]), np.nanmean(A[..., 7] - A[..., 6]), np.nanmean(A[..., 2] - A[..., 7])))
 cta = os.environ.get("FLOW_TRACE_CTA")
 if cta is not None:
     cta = int(cta)
