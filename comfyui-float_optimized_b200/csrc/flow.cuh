@@ -50,7 +50,8 @@ struct FlowParams {
   int n_steps, n_stages, n_gemms;
   int CH, nsub, NPs, n_chunks, RP;     // rows per chunk, chunks per sequence, padded rows per sequence, chunks, padded rows in total
   int nw, na, a_slot_bytes, n_tslots;  // weight ring slots, activation ring slots and their size, TMEM column slots (512 / CH)
-  int tm_ax, gelu_f4;
+  int tm_ax, poll_mode;
+  float fx_c;                          // deterministic split-K: partial sums are rounded to multiples of 2^-k with (v + fx_c) - fx_c; 0 = off
   const FlowGemm* gemms;               // device array [n_gemms]: x_emb, (qkv, proj, fc1, fc2) x depth, dec
   const CUtensorMap* tmaps;
   float *X, *Pacc, *QKVacc, *Hacc, *Vacc;          // padded rows; QKVacc holds two buffers (block parity)
@@ -92,6 +93,14 @@ __device__ __forceinline__ size_t flow_tiled_off(int c, int r, int col, int nkb,
 
 __device__ __forceinline__ void flow_fail(const FlowParams& p, int code) { win_fail(p.err_flag, code); }
 
+// Deterministic split-K.  The K slices of a tile meet in L2 through fp32 reduce-adds in arrival order.  Every partial sum is first
+// rounded to a multiple of the quantum q = 2^-FMT_FLOW_FIXED (two FADDs: (v + C) - C with C = 1.5 * 2^23 * q); sums of multiples of q
+// are exact in fp32 while they stay below 2^24 * q, exact additions are associative, and so the same inputs give the same bits on
+// every run (the reference is bitwise reproducible under fix_noise_seed, nodes_vadv.py:673-689).  q = 2^-14: exact below 1024, each
+// partial moves by at most 3.1e-5 (bf16 rounding of the operands moves a value of 1 by 2e-3).  Beyond the range the additions round
+// as usual: the result stays fp32-accurate and merely loses run-to-run bit equality.
+__device__ __forceinline__ float flow_quantize(const FlowParams& p, float v) { return __fsub_rn(__fadd_rn(v, p.fx_c), p.fx_c); }
+
 __device__ __forceinline__ void flow_mbar_wait(const FlowParams& p, uint64_t* bar, uint32_t parity, int code) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
@@ -100,13 +109,31 @@ __device__ __forceinline__ void flow_mbar_wait(const FlowParams& p, uint64_t* ba
   }
 }
 // spin until the counter has reached `target` (acquire)
-__device__ __forceinline__ void flow_wait_flag(const FlowParams& p, const unsigned* flag, unsigned target, int code) {
-  if (target == 0u) return;
-  if (ld_acquire_gpu(flag) >= target) return;
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// poll_mode 1: relaxed polls (no L1 invalidation per poll - the other engine of the CTA keeps its L1 lines while this one waits) and
+// one acquire load once the counter is complete; poll_mode 0: every poll is an acquire load
+__device__ __forceinline__ int flow_wait_flag(const FlowParams& p, const unsigned* flag, unsigned target, int code) {
+  if (target == 0u) return 0;
+  if (ld_acquire_gpu(flag) >= target) return 1;
   const long long t0 = clock64();
-  while (ld_acquire_gpu(flag) < target) {
-    if (clock64() - t0 > p.spin_limit) flow_fail(p, code);
+  int polls = 2;
+  if (p.poll_mode == 1) {
+    while (ld_relaxed_gpu(flag) < target) {
+      ++polls;
+      if (clock64() - t0 > p.spin_limit) flow_fail(p, code);
+    }
+    (void)ld_acquire_gpu(flag);
+  } else {
+    while (ld_acquire_gpu(flag) < target) {
+      ++polls;
+      if (clock64() - t0 > p.spin_limit) flow_fail(p, code);
+    }
   }
+  return polls;                                  // trace only
 }
 __device__ __forceinline__ unsigned* flow_flag(unsigned* base, const FlowParams& p, int e, int st, int c) {
   return base + (static_cast<size_t>(e) * p.n_gemms + st) * (static_cast<size_t>(p.n_chunks) * FLOW_FLAG_STRIDE) + c * FLOW_FLAG_STRIDE;
@@ -169,7 +196,9 @@ __device__ __forceinline__ void flow_act_loader(const FlowParams& p, const FlowI
         flow_mark(p, e, 0, g, c, 0);
         // dependency: the SIMT stage that produced this chunk of the operand (x-embedder: the CFG combine of the previous evaluation)
         if (g > 0) {
-          flow_wait_flag(p, flow_flag(p.s_done, p, e, g - 1, c), units[kind * FLOW_MAX_CHUNKS + c].n_part, 0x02000000 | (e << 16) | (g << 8) | c);
+          const int polls = flow_wait_flag(p, flow_flag(p.s_done, p, e, g - 1, c), units[kind * FLOW_MAX_CHUNKS + c].n_part, 0x02000000 | (e << 16) | (g << 8) | c);
+          if (p.trace != nullptr && e == p.trace_eval)
+            p.trace[(((static_cast<size_t>(blockIdx.x) * 2) * p.n_gemms + g) * p.n_chunks + c) * 8 + 6] = polls;
         } else if (e > 0) {
           const int cc = chunks[c].clip * p.nsub + chunks[c].sub;          // the combine publishes per (clip, sub-chunk) on branch 0's chunk
           flow_wait_flag(p, flow_flag(p.s_done, p, e - 1, p.n_gemms - 1, cc), units[FK_COMB * FLOW_MAX_CHUNKS + cc].n_part,
@@ -273,6 +302,10 @@ __device__ __forceinline__ void flow_epilogue(const FlowParams& p, const FlowIte
             named_bar_sync(2, 128);
           }
           tmem_ld_wait();
+          if (p.fx_c != 0.f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = flow_quantize(p, v[j]);
+          }
           if (h == nh - 1) {                        // accumulator slot drained: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();

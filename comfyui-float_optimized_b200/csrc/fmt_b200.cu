@@ -98,7 +98,8 @@ struct FmtHandle {
   bool flow_active = false;
   int flow_ch = 64;                              // rows per chunk (FMT_FLOW_CH = 32 | 64)
   int flow_max_rows = 256;                       // plans with more token rows run one kernel per op (FMT_FLOW_MAX_ROWS)
-  int flow_gelu_f4 = 2;                          // float4 per thread and GELU unit (FMT_FLOW_GELU_F4 = 1..4)
+  int flow_fixed = 14;                           // FMT_FLOW_FIXED: split-K partial sums are rounded to multiples of 2^-k before they meet in L2 (exact, order-independent sums below 2^(24-k): bitwise reproducible runs); 0 = off
+  int flow_poll = 1;                             // FMT_FLOW_POLL: 0 = acquire polls, 1 = relaxed polls + one acquire load
   long long flow_spin_limit = 4000000000ll;      // SM clocks a wait may spin before the kernel traps (FMT_FLOW_SPIN_MS)
   FlowParams flow_params{};
   DevBuf flow_gemms, flow_tmaps, flow_acc, flow_act, flow_flags, flow_trace;
@@ -621,7 +622,8 @@ static int setup_flow(FmtHandle* h, cudaStream_t st) {
   fp.n_steps = h->plan.n_steps; fp.n_stages = h->plan.n_stages; fp.n_gemms = n_gemms;
   fp.CH = CH; fp.nsub = (s.N + CH - 1) / CH; fp.NPs = fp.nsub * CH; fp.n_chunks = s.nb * s.B * fp.nsub; fp.RP = fp.n_chunks * CH;
   fp.n_tslots = 512 / CH;
-  fp.gelu_f4 = h->flow_gelu_f4 < 1 ? 1 : h->flow_gelu_f4 > 4 ? 4 : h->flow_gelu_f4;
+  fp.poll_mode = h->flow_poll;
+  fp.fx_c = h->flow_fixed > 0 ? 12582912.f / static_cast<float>(1u << h->flow_fixed) : 0.f;   // 1.5 * 2^23 * 2^-k
   fp.spin_limit = h->flow_spin_limit;
   const size_t RP = fp.RP;
 
@@ -899,7 +901,8 @@ int32_t fmt_create(const FmtDims* dims, const void* const* wp, int32_t n_ptrs, i
   if (const char* e = getenv("FMT_WINDOW")) h->use_window = atoi(e);
   if (const char* e = getenv("FMT_FLOW_CH")) { const int v = atoi(e); if (v == 32 || v == 64) h->flow_ch = v; }
   if (const char* e = getenv("FMT_FLOW_MAX_ROWS")) h->flow_max_rows = atoi(e);
-  if (const char* e = getenv("FMT_FLOW_GELU_F4")) h->flow_gelu_f4 = atoi(e);
+  if (const char* e = getenv("FMT_FLOW_POLL")) h->flow_poll = atoi(e);
+  if (const char* e = getenv("FMT_FLOW_FIXED")) { const int v = atoi(e); if (v >= 0 && v <= 22) h->flow_fixed = v; }
   if (const char* e = getenv("FMT_FLOW_SPIN_MS")) h->flow_spin_limit = static_cast<long long>(atof(e) * 1.9e6);
   if (const char* e = getenv("FMT_WIN_SPG")) h->win_spg = atoi(e);
   if (const char* e = getenv("FMT_WIN_FUSE_GELU")) h->win_fuse_gelu = atoi(e) != 0;
@@ -1213,6 +1216,8 @@ int32_t fmt_sample_clip(FmtHandle* h, const FmtClip* c, void* stream) {
   if (c->location == FMT_LOC_HOST) {
     CUDA_OK(cudaMemcpyAsync(c->r_d, r_d, n_rd * 4, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
+    // the persistent kernels report a tripped bounded spin through a mapped status word (the launch fails as well)
+    if (h->window_active && h->win_err_host && *h->win_err_host != 0) return set_err(-6, "window kernel reported status 0x%08x", *h->win_err_host);
   }
   return 0;
 }

@@ -162,11 +162,13 @@ def test_properties_full_size(pkg):
     assert torch.equal(a, b)                                    # B=4 runs the tiled GEMM path: bitwise deterministic
     for i in (0, 3):                                            # clips never mix: batch of 4 == 4 batches of 1
         s, _ = node.sample_rd_sequence_va(r_s[i:i + 1], wa[i:i + 1], we[i:i + 1], T, model, *args, _noise=noise[:, i:i + 1].contiguous())
-        # B=1 runs the persistent window kernel (split-K partial sums meet in L2 through TMA reduce-add: the summation order
-        # is not fixed, and attention reads fp32 q/k/v) -> equal within bf16 noise, not bitwise
+        # B=1 runs the dataflow window kernel (split-K partial sums, attention on fp32 q/k/v): a different schedule of the same
+        # arithmetic -> equal to the batched run within bf16 noise, not bitwise
         assert cases.max_abs(s, a[i:i + 1]) <= 5e-3, cases.max_abs(s, a[i:i + 1])
         s2, _ = node.sample_rd_sequence_va(r_s[i:i + 1], wa[i:i + 1], we[i:i + 1], T, model, *args, _noise=noise[:, i:i + 1].contiguous())
-        assert cases.max_abs(s, s2) <= 5e-3                     # run-to-run: only the reduce-add summation order may differ
+        # run-to-run: the K slices are rounded to multiples of 2^-14 before they meet in L2, their fp32 sums are exact and so
+        # order-independent: the same seed gives the same bits, as the reference does under fix_noise_seed (nodes_vadv.py:673-689)
+        assert torch.equal(s, s2)
     args1 = (2.0, 1.0, 1.0, False, 1, "euler", 1e-5, 1e-5, 0.1, 0.1, 0.1, True, 3)
     n1, _ = node.sample_rd_sequence_va(r_s, wa, we, T, model, *args1, _noise=noise)
     assert torch.equal(n1, torch.cat(list(noise), dim=1)[:, :T])  # nfe=1: the solver returns the noise unchanged

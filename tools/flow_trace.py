@@ -30,7 +30,7 @@ n = be.lib.fmt_debug_window_trace(be._handle, None, 0)
 buf = np.zeros(n, dtype=np.int64)
 be.lib.fmt_debug_window_trace(be._handle, buf.ctypes.data_as(C.c_void_p), n)
 n_cta = torch.cuda.get_device_properties(0).multi_processor_count
-CH = int(os.environ.get("FMT_FLOW_CH", "32"))
+CH = int(os.environ.get("FMT_FLOW_CH", "64"))
 n_gemms = 2 + 4 * d.fmt_depth
 nsub = -(-(d.num_prev_frames + d.frames_per_clip) // CH)
 n_chunks = 3 * B * nsub
@@ -42,8 +42,11 @@ T_ns = float(np.median(cal[:, 1, 0] - cal[:, 0, 0]))
 freq = dclk / T_ns                                                            # SM clocks per ns, per CTA
 print("SM clock %.4f .. %.4f GHz; kernel %.1f us" % (freq.min(), freq.max(), T_ns / 1e3))
 t = np.where(tr > 0, (tr - cal[:, 0, 1][:, None, None, None, None]) / freq[:, None, None, None, None], np.nan)
+t[:, 0, :, :, 6] = np.nan
 t0 = np.nanmin(t)
 t = (t - t0) / 1e3                                                             # us since the first stamp of the traced evaluation
+np.savez_compressed(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "flow_trace_%s.npz" % os.environ.get("FLOW_TRACE_TAG", "t")),
+                    t=t, raw=tr, n_gemms=n_gemms, n_chunks=n_chunks)   # [cta][engine][stage][chunk][slot] in us, for offline analysis
 names = ["x_emb", "qkv", "proj", "fc1", "fc2"]
 snames = ["row0"] + ["attn", "row", "gelu", "row2"] * d.fmt_depth + ["comb"]
 
@@ -115,3 +118,24 @@ if cta is not None:
     for v, s_ in ev:
         if lo <= v <= hi:
             print(f"{v:9.2f}  {s_}")
+# ---- spread over CTAs: when the items of a (stage, chunk) published / when its SIMT units released, relative to the first one (quantiles, mean over block stages)
+with np.errstate(all="ignore"):
+    def spread(x):   # x: [cta, stage, chunk]
+        lo = np.nanmin(x, axis=0, keepdims=True)
+        q = np.nanpercentile(x - lo, [10, 50, 90, 100], axis=0)          # [4, stage, chunk]
+        return np.nanmean(q, axis=(1, 2))
+    print("\nspread over CTAs relative to the earliest (10 / 50 / 90 / 100 %%): GEMM dep ok %s | acc ready %s | published %s" % (
+        np.round(spread(G[..., 1]), 2), np.round(spread(G[..., 3]), 2), np.round(spread(G[..., 5]), 2)))
+    print("                                                              SIMT ok %s | work done %s | released %s" % (
+        np.round(spread(S[..., 1]), 2), np.round(spread(S[..., 2]), 2), np.round(spread(S[..., 4]), 2)))
+    polls = tr[:, 0, 1:n_gemms - 1, :, 6]
+    waited = (G[..., 1] - G[..., 0])
+    m = polls > 2
+    print("loader polls per flag wait: mean %.1f; poll period (waits with > 2 polls) %.3f us" % (np.mean(polls[polls > 0]), np.nanmean(waited[m] / (polls[m] - 1))))
+    # which CTAs publish last?  rank of each CTA's publish time per (stage, chunk), averaged
+    rk = np.argsort(np.argsort(np.where(np.isnan(G[..., 5]), 1e9, G[..., 5]), axis=0), axis=0).astype(np.float64)
+    rk[np.isnan(G[..., 5])] = np.nan
+    mean_rank = np.nanmean(rk, axis=(1, 2))
+    order = np.argsort(-np.nan_to_num(mean_rank))
+    print("CTAs that publish latest on average (cta: mean rank of %d): %s" % (n_cta, ", ".join(f"{c_}:{mean_rank[c_]:.0f}" for c_ in order[:12])))
+    print("CTAs that publish earliest: %s" % ", ".join(f"{c_}:{mean_rank[c_]:.0f}" for c_ in order[-8:]))

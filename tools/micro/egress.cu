@@ -5,6 +5,7 @@
 //   mode 3: st.global.v8.f32 (256-bit), 1 KB per warp instruction
 //   mode 4: red.global.add.v4.f32 (LSU vector reds), 512 B per warp instruction
 //   mode 5: st.global.f32 scalar coalesced (128 B per warp instruction)
+//   mode 6: cp.reduce.async.bulk .add.s32 (the deterministic fixed-point split-K)
 // `share` CTAs target the same region (split-K partials of one tile meet there); share = 1: every CTA has its own slot.
 #include <cstdio>
 #include <cstdint>
@@ -15,6 +16,9 @@
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_reduce_add(float* dst, const void* src, uint32_t bytes) {
   asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_reduce_add_s32(float* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.s32 [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_store(float* dst, const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
@@ -33,11 +37,11 @@ __global__ void __launch_bounds__(512, 1) k(float* dst, int bytes, int share, in
   for (int it = 0; it < iters; ++it) {
     __syncthreads();
     const long long t0 = clock64();
-    if (mode <= 1) {
+    if (mode <= 1 || mode == 6) {
       if (tid == 0) {
         for (int o = 0; o < bytes; o += 16384) {
           const int n = min(16384, bytes - o);
-          if (mode == 0) bulk_reduce_add(base + o / 4, smem + o, n); else bulk_store(base + o / 4, smem + o, n);
+          if (mode == 0) bulk_reduce_add(base + o / 4, smem + o, n); else if (mode == 6) bulk_reduce_add_s32(base + o / 4, smem + o, n); else bulk_store(base + o / 4, smem + o, n);
           bulk_commit();
         }
         bulk_wait0();
@@ -68,13 +72,13 @@ int main(int argc, char** argv) {
   cudaMalloc(&dst, (size_t)148 * 256 * 1024); cudaMalloc(&out, 148 * 8);
   cudaMemset(dst, 0, (size_t)148 * 256 * 1024);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-  const char* names[] = {"TMA reduce-add", "TMA store", "st.v4", "st.v8", "red.v4", "st.f32"};
+  const char* names[] = {"TMA reduce-add", "TMA store", "st.v4", "st.v8", "red.v4", "st.f32", "TMA red s32"};
   printf("%-15s %6s %5s %5s %4s | %9s %9s %9s\n", "path", "KB/SM", "share", "thr", "CTAs", "us median", "us max", "GB/s/SM");
   for (int bytes : {48 * 1024, 96 * 1024})
-    for (int mode = 0; mode < 6; ++mode)
+    for (int mode : {0, 6, 1})
       for (int share : {1, 6})
         for (int nthreads : {128, 256, 512}) {
-          if (mode <= 1 && nthreads != 128) continue;
+          if ((mode <= 1 || mode == 6) && nthreads != 128) continue;
           if ((mode == 2 || mode == 3 || mode == 5) && share != 1) continue;
           for (int grid : {148, 32}) {
             for (int rep = 0; rep < 2; ++rep) k<<<grid, 512, 128 * 1024>>>(dst, bytes, share, mode, iters, nthreads, out);
