@@ -46,10 +46,14 @@ def peaks():
 
 
 def measured_traffic(key):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r01_traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(p):
-        return json.load(open(p)).get(key, {})
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` captures (profiles/r02_traffic.json,
+    else round 1's)."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            rec = json.load(open(p)).get(key)
+            if rec:
+                return rec
     return {}
 
 
@@ -256,7 +260,9 @@ def roofline_record(dims, B, T, t_step, n_win, pk):
     hbm_frac, tf_frac = hbm_achieved / pk["hbm_gbs"], tf_achieved / pk["bf16_tflops_sustained"]
     # Which roofline binds is a property of the workload: <= 2 clips stream the weights (180 flop/B per clip
     # against a ridge of ~210), >= 8 clips are dense-contraction bound.
-    prof = measured_traffic("b1_window" if work["rows"] <= 256 else "b32")
+    # <= 256 token rows run the persistent window kernel: the dataflow kernel (csrc/flow.cuh) unless FMT_WINDOW selects round 1's
+    small = "b1_flow" if os.environ.get("FMT_WINDOW", "3") == "3" else "b1_window"
+    prof = measured_traffic(small if work["rows"] <= 256 else "b32")
     if work["rows"] <= 512:
         roof = dict(bound="hbm", achieved=hbm_achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=hbm_frac, traffic=prof.get("dram_bytes_per_launch"))
     else:
