@@ -180,6 +180,41 @@ def time_gpu_eager_baseline(W, dims, B, T, dev, reps=3):
                 ms_per_ode_step=1e3 * best / (n_win * (NFE - 1)))
 
 
+def measure_handoff(pkg, model, dims, B, T, dev, iters=10):
+    """FloatApplyAudioProjection -> sampler node, end to end from CPU wav2vec features to CPU motion latents,
+    with the reference's CPU hand-off between the two nodes (nodes_vadv.py:197,692-694) and with the device-resident one
+    (keep_on_device).  Wall clock, synchronised; bf16 mode."""
+    synth = pkg.synth
+    layer = pkg.AudioProjectionLayer(9216, dims.dim_w, target_device=dev)
+    g = torch.Generator().manual_seed(62)
+    with torch.no_grad():
+        for prm in layer.parameters():
+            prm.copy_(torch.randn(prm.shape, generator=g) * (0.01 if prm.ndim == 2 else 0.1) + (1.0 if prm.ndim == 1 and prm is layer[1].weight else 0.0))
+    feats = synth.synth_wav2vec_features(B, T, 9216, seed=5).pin_memory()
+    r_s, _, we = workload_inputs(dims, B, T, 0)
+    r_s, we = r_s.pin_memory(), we.pin_memory()
+    proj, samp = pkg.FloatApplyAudioProjection(), pkg.FloatSampleMotionSequenceRD_VA()
+    args = (A_CFG, R_CFG, E_CFG, False, NFE, "euler", 1e-5, 1e-5, 0.1, 0.1, 0.1, True, 15)
+    out = {}
+    for keep in (False, True):
+        def run():
+            (wa,) = proj.apply_projection(feats, layer, keep_on_device=keep)
+            r_d, _ = samp.sample_rd_sequence_va(r_s, wa, we, T, model, *args)
+            return r_d
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            run()
+        torch.cuda.synchronize()
+        out["device_resident_ms" if keep else "cpu_handoff_ms"] = 1e3 * (time.perf_counter() - t0) / iters
+    out.update(workload=f"{B} clip(s) x {T} frames: CPU wav2vec features (B, T, 9216) -> FloatApplyAudioProjection -> "
+                        "FloatSampleMotionSequenceRD_VA -> CPU latents", handoff_bytes=B * T * dims.dim_w * 4,
+               value=B * T / (out["device_resident_ms"] * 1e-3), unit="frames/s")
+    return out
+
+
 def measure_product(pkg, be, model, dims, B, T, rank, world, dev, dist, steps, warmup, e2e_iters):
     """Times the product path on this rank's B clips x T frames: resident (CUDA events) and end to end (node, CPU tensors)."""
     L = dims.frames_per_clip
@@ -379,6 +414,11 @@ def main():
                gpu_launches=m["launches"], graph_kernel_nodes=graph_nodes, window_kernel_status=m["window_kernel"], roofline=roof, clocks=m["clocks"])
     if large is not None:
         res["large_batch"] = large
+    if world == 1 and B <= 32:
+        try:
+            res["handoff"] = measure_handoff(pkg, model, dims, B, T, dev)
+        except Exception as e:
+            res["handoff"] = dict(error=f"{type(e).__name__}: {e}"[:300])
     if not args.no_cpu_baseline and world == 1:
         res["cpu_baseline"] = time_cpu_baseline(W, dims, B, T, budget_s=25.0)
         if B <= 32:

@@ -7,6 +7,7 @@ accumulation, then LayerNorm (affine) and SiLU in fp32.  No CPU / eager fallback
 """
 import ctypes as C
 import logging
+import os
 import weakref
 
 import torch
@@ -121,14 +122,16 @@ class FloatApplyAudioProjection:
                 "wav2vec_features": ("TORCH_TENSOR", {
                     "tooltip": "The batch of interpolated feature tensors output by the Wav2Vec feature extraction node."}),
                 "projection_layer": ("AUDIO_PROJECTION_LAYER", {"tooltip": "The loaded audio projection layer module."}),
-            }
+            },
+            # B200 addition: hand wa_latent to the sampler node as a CUDA tensor (default: CPU between nodes, as the reference)
+            "optional": {"keep_on_device": ("BOOLEAN", {"default": False, "tooltip": "Return wa_latent as a CUDA tensor instead of moving it to the CPU."})},
         }
 
     RETURN_TYPES = ("TORCH_TENSOR",)
     RETURN_NAMES = ("wa_latent",)
     FUNCTION = "apply_projection"
 
-    def apply_projection(self, wav2vec_features: torch.Tensor, projection_layer: torch.nn.Module, _mode="bf16"):
+    def apply_projection(self, wav2vec_features: torch.Tensor, projection_layer: torch.nn.Module, keep_on_device=None, _mode="bf16"):
         # validation and messages as in nodes_vadv.py:170-181
         if not isinstance(wav2vec_features, torch.Tensor):
             raise TypeError("Input 'wav2vec_features' must be a torch.Tensor.")
@@ -146,4 +149,7 @@ class FloatApplyAudioProjection:
         logger.info(f"Applying audio projection layer to features of shape {features_on_device.shape}.")
         wa_latent_gpu = be.apply(features_on_device, mode=_mode)
         logger.info(f"Output wa_latent shape: {wa_latent_gpu.shape}")
-        return (wa_latent_gpu.cpu(),)        # CPU between nodes, as the reference (nodes_vadv.py:197)
+        if keep_on_device is None:
+            keep_on_device = os.environ.get("FMT_KEEP_ON_DEVICE", "0") not in ("", "0", "false", "False")
+        # CPU between nodes, as the reference (nodes_vadv.py:197), unless the device-resident hand-off was asked for
+        return (wa_latent_gpu if keep_on_device else wa_latent_gpu.cpu(),)

@@ -36,6 +36,24 @@ PRECISION_WIDGET = (("default",) + PRECISION_MODES, {"default": "default", "tool
                                                      "(validation mode, matches the reference to 1e-4). default = $FMT_MODE or bf16."})
 
 
+# Second optional widget (second half): the reference moves every tensor back to the CPU between nodes
+# (nodes_vadv.py:197,719) and the next node moves it to the GPU again (:692-694).  With keep_on_device the B200 nodes hand CUDA
+# tensors to one another - inputs are accepted on either device anyway.  Default False = the reference's behaviour (drop-in);
+# FMT_KEEP_ON_DEVICE=1 changes the default.
+KEEP_ON_DEVICE_WIDGET = ("BOOLEAN", {"default": False, "tooltip": "Return the result as a CUDA tensor instead of moving it to the CPU "
+                                     "(skips the device->host->device round trip between B200 nodes)."})
+
+
+def keep_on_device_default() -> bool:
+    import os
+    return os.environ.get("FMT_KEEP_ON_DEVICE", "0") not in ("", "0", "false", "False")
+
+
+def _hand_over(t: torch.Tensor, keep_on_device) -> torch.Tensor:
+    keep = keep_on_device_default() if keep_on_device is None else bool(keep_on_device)
+    return t if keep else t.cpu()
+
+
 def _active_mode(precision, _mode):
     mode = resolve_mode(_mode if _mode is not None else precision)
     logger.info(f"B200 FMT sampler: precision mode {mode}")
@@ -73,7 +91,7 @@ class FloatSampleMotionSequenceRD_VA:
                 "fix_noise_seed": ("BOOLEAN", {"default": o.fix_noise_seed}),
                 "seed": ("INT", {"default": o.seed, "min": 0, "max": 0xffffffffffffffff}),
             },
-            "optional": {"precision": PRECISION_WIDGET},
+            "optional": {"precision": PRECISION_WIDGET, "keep_on_device": KEEP_ON_DEVICE_WIDGET},
         }
 
     RETURN_TYPES = ("TORCH_TENSOR", "FLOAT_FMT_MODEL")
@@ -83,7 +101,7 @@ class FloatSampleMotionSequenceRD_VA:
     def sample_rd_sequence_va(self, r_s_latent, wa_latent, we_latent, audio_num_frames, float_fmt_model,
                               a_cfg_scale, r_cfg_scale, e_cfg_scale, include_r_cfg, nfe, torchdiffeq_ode_method,
                               ode_atol, ode_rtol, audio_dropout_prob, ref_dropout_prob, emotion_dropout_prob,
-                              fix_noise_seed, seed, precision="default", _mode=None, _noise=None):
+                              fix_noise_seed, seed, precision="default", keep_on_device=None, _mode=None, _noise=None):
         # window geometry from the options the FMT was built with (nodes_vadv.py:627-645)
         src = BaseOptions()
         fco = getattr(float_fmt_model, "final_construction_options", None)
@@ -128,8 +146,7 @@ class FloatSampleMotionSequenceRD_VA:
                 target_device=target_device, a_cfg_scale=a_cfg_scale, r_cfg_scale=r_cfg_scale, e_cfg_scale=e_cfg_scale,
                 include_r_cfg=include_r_cfg, noise_seed_generator=noise_gen, progress_bar=_progress_bar(n_windows),
                 mode=_active_mode(precision, _mode), noise=_noise)
-            r_d_cpu = r_d.cpu()
-            return (r_d_cpu, float_fmt_model)
+            return (_hand_over(r_d, keep_on_device), float_fmt_model)    # CPU between nodes unless asked otherwise (nodes_vadv.py:719)
         except Exception as e:
             logger.error(f"Error during VA ODE sampling: {e}")
             raise
@@ -156,7 +173,7 @@ class FloatSampleMotionSequenceRD:
                 "e_cfg_scale": ("FLOAT", {"default": 1.0, "min": 0.0, "max": 10.0, "step": 0.1}),
                 "seed": ("INT", {"default": 62064758300528, "min": 0, "max": 0xffffffffffffffff}),
             },
-            "optional": {"precision": PRECISION_WIDGET},
+            "optional": {"precision": PRECISION_WIDGET, "keep_on_device": KEEP_ON_DEVICE_WIDGET},
         }
 
     RETURN_TYPES = ("TORCH_TENSOR", "FLOAT_PIPE")
@@ -164,7 +181,7 @@ class FloatSampleMotionSequenceRD:
     FUNCTION = "sample_rd_sequence"
 
     def sample_rd_sequence(self, r_s_latent, wa_latent, audio_num_frames, we_latent, float_pipe, a_cfg_scale, e_cfg_scale, seed,
-                           precision="default", _mode=None, _noise=None):
+                           precision="default", keep_on_device=None, _mode=None, _noise=None):
         agent = float_pipe
         opt = agent.opt
         if not all(isinstance(t, torch.Tensor) for t in [r_s_latent, wa_latent, we_latent]):
@@ -194,7 +211,7 @@ class FloatSampleMotionSequenceRD:
             ode_method=opt.torchdiffeq_ode_method, ode_atol=opt.ode_atol, ode_rtol=opt.ode_rtol, target_device=device,
             a_cfg_scale=a_cfg_scale, r_cfg_scale=opt.r_cfg_scale, e_cfg_scale=e_cfg_scale, include_r_cfg=False,
             noise_seed_generator=noise_gen, progress_bar=_progress_bar(n_windows), mode=_active_mode(precision, _mode), noise=_noise)
-        return (r_d.cpu(), float_pipe)
+        return (_hand_over(r_d, keep_on_device), float_pipe)
 
 
 EMOTIONS = ['none', 'angry', 'disgust', 'fear', 'happy', 'neutral', 'sad', 'surprise']     # nodes.py:27

@@ -377,3 +377,70 @@ def test_audio_projection_full_size(pkg):
     assert pkg.projection_backend_for(layer, DEV) is be and be.launch_count() >= 6
     out32 = be.apply(x[:4], "fp32")
     assert cases.rel_err(out32.cpu(), ref[:4].cpu()) <= 1e-4
+
+
+def test_device_resident_handoff(pkg):
+    """SURVEY.md 8f rank 2, second half: FloatApplyAudioProjection -> sampler node without the device -> host -> device round
+    trip the reference makes between nodes (nodes_vadv.py:197,692-694,719).  keep_on_device hands CUDA tensors over; the result
+    is bit-identical to the CPU hand-off (the default, which stays the reference's behaviour)."""
+    from oracle.synth import synth_wav2vec_features
+    d = cases.FmtDims()
+    model = model_for(pkg, "full")
+    rec = dict(in_dim=9216, seed=62)
+    layer = _projection_layer(pkg, rec)
+    B, T = 2, 100
+    feats = synth_wav2vec_features(B, T, 9216, seed=9)
+    r_s, _, we = pkg.synth.synth_inputs(d, B, T, seed=7)
+    g = torch.Generator().manual_seed(15)
+    noise = torch.stack([torch.randn(B, d.frames_per_clip, d.dim_w, generator=g) for _ in range(2)])
+    proj, samp = pkg.FloatApplyAudioProjection(), pkg.FloatSampleMotionSequenceRD_VA()
+    args = (2.0, 1.0, 1.0, False, 4, "euler", 1e-5, 1e-5, 0.1, 0.1, 0.1, True, 15)
+    (wa_cpu,) = proj.apply_projection(feats, layer)
+    assert wa_cpu.device.type == "cpu"
+    out_cpu, _ = samp.sample_rd_sequence_va(r_s, wa_cpu, we, T, model, *args, _noise=noise)
+    assert out_cpu.device.type == "cpu"
+    (wa_dev,) = proj.apply_projection(feats, layer, keep_on_device=True)
+    assert wa_dev.is_cuda and torch.equal(wa_dev.cpu(), wa_cpu)
+    out_dev, _ = samp.sample_rd_sequence_va(r_s.to(DEV), wa_dev, we.to(DEV), T, model, *args, keep_on_device=True, _noise=noise.to(DEV))
+    assert out_dev.is_cuda and torch.equal(out_dev.cpu(), out_cpu)
+
+
+def test_configs2_sixty_second_clip(pkg):
+    """BASELINE.json configs[2] at full size: one 60 s clip = 1500 frames = 30 sequential windows chained through prev_x / prev_wa,
+    free-running against the oracle on the same device and noise (270 dependent ODE steps)."""
+    d = cases.FmtDims()
+    model = model_for(pkg, "full")
+    T, nfe = 1500, 10
+    r_s, wa, we = pkg.synth.synth_inputs(d, 1, T, seed=41)
+    g = torch.Generator().manual_seed(6)
+    noise = torch.stack([torch.randn(1, d.frames_per_clip, d.dim_w, generator=g) for _ in range(30)])
+    out, _ = pkg.FloatSampleMotionSequenceRD_VA().sample_rd_sequence_va(r_s, wa, we, T, model, 2.0, 1.0, 1.0, False, nfe, "euler", 1e-5, 1e-5,
+                                                                       0.1, 0.1, 0.1, True, 6, _noise=noise)
+    ref = _oracle_on_gpu(d, r_s, wa, we, T, noise, nfe=nfe, a_cfg_scale=2.0, r_cfg_scale=1.0, e_cfg_scale=1.0)
+    assert out.shape == ref.shape == (1, T, d.dim_w)
+    per_window = [cases.max_abs(out[:, s:s + 50], ref[:, s:s + 50]) for s in range(0, T, 50)]
+    assert max(per_window) <= 2e-2, per_window
+    assert max(per_window[15:]) <= 4 * max(max(per_window[:15]), 1e-3), per_window      # no blow-up along the chain
+
+
+def test_configs3_full_batch(pkg):
+    """BASELINE.json configs[3] at its single-GPU batch: 256 independent clips in one call (46 080 token rows per evaluation, CTA-pair
+    GEMMs, chunked AdaLN tables), one window, nfe 4 to keep the oracle short; against the oracle on the same device and noise."""
+    d = cases.FmtDims()
+    model = model_for(pkg, "full")
+    B, T, nfe = 256, 50, 4
+    r_s, wa, we = pkg.synth.synth_inputs(d, B, T, seed=321)
+    g = torch.Generator().manual_seed(12)
+    noise = torch.stack([torch.randn(B, d.frames_per_clip, d.dim_w, generator=g)])
+    out, _ = pkg.FloatSampleMotionSequenceRD_VA().sample_rd_sequence_va(r_s, wa, we, T, model, 2.0, 1.0, 1.0, False, nfe, "euler", 1e-5, 1e-5,
+                                                                       0.1, 0.1, 0.1, True, 12, _noise=noise)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    Wd = {k: v.to(DEV) for k, v in cases.weights("full").items()}
+    ref = torch.empty(B, T, d.dim_w)
+    with torch.no_grad():
+        for b0 in range(0, B, 64):                               # the eager oracle in slices of 64 clips (clips never mix)
+            sl = slice(b0, b0 + 64)
+            ref[sl] = O.sample_loop(Wd, d, r_s[sl].to(DEV), wa[sl].to(DEV), we[sl].to(DEV), T, nfe=nfe, a_cfg_scale=2.0, r_cfg_scale=1.0,
+                                    e_cfg_scale=1.0, noise=noise[:, sl].to(DEV)).cpu()
+    assert out.shape == (B, T, d.dim_w) and torch.isfinite(out).all()
+    assert cases.max_abs(out, ref) <= 2e-2, cases.max_abs(out, ref)

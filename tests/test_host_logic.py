@@ -126,9 +126,13 @@ def test_node_surface_matches_reference(pkg):
     assert fp.RETURN_TYPES == ("IMAGE", "AUDIO", "FLOAT") and fp.RETURN_NAMES == ("images", "ref_audio", "fps") and fp.CATEGORY == "FLOAT"
     assert list(fp.INPUT_TYPES()["required"]) == ["ref_image", "ref_audio", "float_pipe", "a_cfg_scale", "e_cfg_scale", "fps", "emotion",
                                                   "face_align", "seed"]
-    # the one widget this backend adds is optional, so saved reference workflows load unchanged
-    for cls in (va, adv, fp):
-        assert list(cls.INPUT_TYPES()["optional"]) == ["precision"]
+    # the widgets this backend adds are optional, so saved reference workflows load unchanged; keep_on_device defaults to the
+    # reference's behaviour (CPU tensors between nodes)
+    for cls in (va, adv):
+        assert list(cls.INPUT_TYPES()["optional"]) == ["precision", "keep_on_device"]
+        assert cls.INPUT_TYPES()["optional"]["keep_on_device"][1]["default"] is False
+    assert list(fp.INPUT_TYPES()["optional"]) == ["precision"]
+    assert list(ap.INPUT_TYPES()["optional"]) == ["keep_on_device"] and ap.INPUT_TYPES()["optional"]["keep_on_device"][1]["default"] is False
 
 
 @pytest.mark.refimpl
