@@ -735,13 +735,21 @@ static int launch_flow_nv(FmtHandle* h, cudaStream_t st, bool probe_only) {
   int occ = 0;
   CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fmt_flow_kernel<NV>, FLOW_THREADS, smem));
   REQUIRE(occ >= 1, "flow kernel does not fit on an SM (%d B smem)", smem);
-  if (probe_only) return 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(h->num_sms); cfg.blockDim = dim3(FLOW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attrs[1];
   attrs[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: they wait for one another's counters
   attrs[0].val.cooperative = 1;
   cfg.attrs = attrs; cfg.numAttrs = 1;
+  if (probe_only) {
+    // one trial launch with zero evaluations (every role loop is empty): under MPS with an SM limit, a green context or any other
+    // reason the runtime cannot make num_sms CTAs co-resident, THIS is where it says so - and the plan runs one kernel per op instead
+    FlowParams trial = h->flow_params;
+    trial.n_steps = 0; trial.trace = nullptr;
+    CUDA_OK(cudaLaunchKernelEx(&cfg, fmt_flow_kernel<NV>, trial));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+  }
   CUDA_OK(cudaLaunchKernelEx(&cfg, fmt_flow_kernel<NV>, h->flow_params));
   count_launch(h);
   return 0;
@@ -1071,9 +1079,22 @@ int32_t fmt_configure(FmtHandle* h, const FmtPlan* p, void* stream) {
   const size_t ts = p->mode == FMT_MODE_BF16 ? 2 : 4;
   h->tsize = ts;
   const size_t R = h->R, U = h->U, H = s.H;
-  // table chunking: keep at most ~48 GB of AdaLN tables resident
+  // table chunking: the AdaLN tables of as many evaluations as fit in half of the memory that is free right now (what this handle
+  // already holds for its tables counts as free: dev_alloc reuses it), at most 48 GB.  ComfyUI keeps the decoder and wav2vec models
+  // on the same GPU, so a fixed cap could fail where the reference, with O(1 step) memory, succeeds; FMT_TABLE_GB overrides.
   const size_t per_eval = U * static_cast<size_t>(h->NT) * ts;
-  size_t chunk = per_eval ? (static_cast<size_t>(48) << 30) / per_eval : 1;
+  size_t cap = static_cast<size_t>(48) << 30;
+  {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      const size_t avail = (free_b + h->table.bytes + h->silu.bytes) / 2;
+      if (avail < cap) cap = avail;
+    } else {
+      (void)cudaGetLastError();
+    }
+    if (const char* e = getenv("FMT_TABLE_GB")) { const double gb = atof(e); if (gb > 0) cap = static_cast<size_t>(gb * (1u << 30)); }
+  }
+  size_t chunk = per_eval ? cap / per_eval : 1;
   if (chunk < 1) chunk = 1;
   if (chunk > static_cast<size_t>(ne > 0 ? ne : 1)) chunk = ne > 0 ? ne : 1;
   h->table_chunk = static_cast<int>(chunk);

@@ -78,6 +78,45 @@ def test_schedule_reproduces_torchdiffeq_fixed_grid(pkg, method, nfe):
     assert torch.allclose(y, ref, rtol=1e-6, atol=1e-7), (y - ref).abs().max()
 
 
+@pytest.mark.parametrize("method,order", [("euler", 1), ("midpoint", 2), ("heun2", 2), ("heun3", 3), ("rk4", 4)])
+def test_solver_tableaux_satisfy_the_order_conditions(pkg, method, order):
+    """torchdiffeq is not installed here, so the fixtures of the non-Euler solvers come from a restatement of its fixed-grid
+    steppers (tests/golden/refshim.py).  This test pins the tableaux to something that restatement cannot influence: the
+    Runge-Kutta order conditions of the method each name stands for (explicit midpoint, Heun's 2nd- and 3rd-order methods, the
+    3/8-rule RK4 of torchdiffeq's rk4_alt_step_func), and the observed convergence order on an ODE with a closed-form solution."""
+    import numpy as np
+    from float_fmt_b200.sampler import SOLVERS
+    t = SOLVERS[method]
+    a, b, c = np.array(t["a"], dtype=np.float64), np.array(t["b"], dtype=np.float64), np.array(t["c"], dtype=np.float64)
+    assert np.allclose(np.triu(a), 0)                                   # explicit
+    assert np.allclose(a.sum(1), c) and np.isclose(b.sum(), 1.0)        # row-sum condition, order 1
+    if order >= 2:
+        assert np.isclose(b @ c, 1 / 2)
+    if order >= 3:
+        assert np.isclose(b @ c ** 2, 1 / 3) and np.isclose(b @ a @ c, 1 / 6)
+    if order >= 4:
+        assert np.isclose(b @ c ** 3, 1 / 4) and np.isclose((b * c) @ a @ c, 1 / 8)
+        assert np.isclose(b @ a @ c ** 2, 1 / 12) and np.isclose(b @ a @ a @ c, 1 / 24)
+    if order < 4:                                                       # ... and not one order more
+        nxt = {1: np.isclose(b @ c, 1 / 2), 2: np.isclose(b @ c ** 2, 1 / 3) and np.isclose(b @ a @ c, 1 / 6),
+               3: np.isclose(b @ c ** 3, 1 / 4) and np.isclose((b * c) @ a @ c, 1 / 8)}[order]
+        assert not nxt
+    # observed order on y' = -2 t y^2, y(0) = 1  ->  y(t) = 1 / (1 + t^2), through the schedule the C ABI receives
+    def err(nfe):
+        s_ = pkg.build_schedule(nfe, method)
+        G, y = s_["n_stages"], 1.0
+        for i in range(s_["n_steps"]):
+            ks = []
+            for g in range(G):
+                yg = y + s_["dt"][i] * sum(s_["a"][g * G + j] * ks[j] for j in range(g))
+                tg = s_["t_eval"][i * G + g]
+                ks.append(-2.0 * tg * yg * yg)
+            y = y + s_["dt"][i] * sum(s_["b"][j] * ks[j] for j in range(G))
+        return abs(y - 0.5)
+    e1, e2 = err(11), err(21)
+    assert abs(np.log2(e1 / e2) - order) < 0.35, (e1, e2)
+
+
 def test_unknown_solver_raises(pkg):
     with pytest.raises(ValueError):
         pkg.build_schedule(10, "dopri5")
