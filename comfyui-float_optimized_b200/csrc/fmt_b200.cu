@@ -348,7 +348,7 @@ static int launch_attn(FmtHandle* h, cudaStream_t st) {
     if (n_seq * heads >= 2 * h->num_sms && tile_smem <= 48 * 1024 && (hd == 64 || hd == 128)) {
       const bf16* q16 = reinterpret_cast<const bf16*>(qkv);
       bf16* o16 = reinterpret_cast<bf16*>(out);
-      const dim3 tg(n_seq * heads), tb(128);
+      const dim3 tg(n_seq * heads), tb(ATTN_TILE_THREADS);
       if (hd == 64) return launch(h, band_attention_tile_kernel<64>, tg, tb, tile_smem, st, 1, q16, s.N, heads, win, scale, o16);
       return launch(h, band_attention_tile_kernel<128>, tg, tb, tile_smem, st, 1, q16, s.N, heads, win, scale, o16);
     }

@@ -285,9 +285,10 @@ __device__ __forceinline__ void bf16x8_to_f32(const int4& t, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
 }
+constexpr int ATTN_TILE_THREADS = 256;
 template <int HD /* head_dim: 64 or 128 */>
-__global__ void __launch_bounds__(128) band_attention_tile_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int heads, int window, float scale,
-                                                                   __nv_bfloat16* __restrict__ out) {
+__global__ void __launch_bounds__(ATTN_TILE_THREADS) band_attention_tile_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int heads, int window, float scale,
+                                                                                 __nv_bfloat16* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t attn_smem[];
   constexpr int hd = HD, NCH = HD / 64;                         // 16-byte chunks per lane
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(attn_smem);
@@ -311,13 +312,18 @@ __global__ void __launch_bounds__(128) band_attention_tile_kernel(const __nv_bfl
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane >> 3, dl = lane & 7;                     // row within the warp's group of 4, dim chunk
-  for (int i0 = warp * 4; i0 < N; i0 += 16) {
+  const int rows_per_pass = (blockDim.x >> 5) * 4;
+  for (int i0 = warp * 4; i0 < N; i0 += rows_per_pass) {
     const int i = i0 + sub;
     const bool valid = i < N;
     const int ic = valid ? i : N - 1;
     float q[NCH][8];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) bf16x8_to_f32(*reinterpret_cast<const int4*>(sQ + ic * hd + c * 64 + dl * 8), q[c]);
+    for (int c = 0; c < NCH; ++c) {
+      bf16x8_to_f32(*reinterpret_cast<const int4*>(sQ + ic * hd + c * 64 + dl * 8), q[c]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) q[c][k] *= scale;
+    }
     const int j0 = max(0, ic - window), j1 = min(N - 1, ic + window);
     float mx = -INFINITY, den = 0.f, acc[NCH][8];
 #pragma unroll
@@ -347,27 +353,37 @@ __global__ void __launch_bounds__(128) band_attention_tile_kernel(const __nv_bfl
       for (int o = 4; o > 0; o >>= 1)
 #pragma unroll
         for (int t = 0; t < KB; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], o);
+      // two-pass softmax over the batch (independent exponentials); batches are merged online only for bands wider than KB keys
+      float bm = -INFINITY;
 #pragma unroll
       for (int t = 0; t < KB; ++t) {
-        if (jb + t <= j1) {
-          const float sc = s[t] * scale;
-          const float nmx = fmaxf(mx, sc);
-          const float corr = expf(mx - nmx), p = expf(sc - nmx);
-          den = den * corr + p;
-          mx = nmx;
-          const int j = jb + t;
+        if (jb + t > j1) s[t] = -INFINITY;
+        bm = fmaxf(bm, s[t]);
+      }
+      if (bm == -INFINITY) continue;                            // a batch past this row's band (another row of the warp is wider)
+      const float nmx = fmaxf(mx, bm);
+      const float corr = __expf(mx - nmx);
+      float p[KB], ps = 0.f;
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            float vv[8];
-            bf16x8_to_f32(*reinterpret_cast<const int4*>(sV + j * hd + c * 64 + dl * 8), vv);
+      for (int t = 0; t < KB; ++t) { p[t] = __expf(s[t] - nmx); ps += p[t]; }
+      den = fmaf(den, corr, ps);
+      mx = nmx;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[c][k] = fmaf(acc[c][k], corr, p * vv[k]);
-          }
+      for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[c][k] *= corr;
+#pragma unroll
+        for (int t = 0; t < KB; ++t) {
+          const int j = min(jb + t, j1);                        // p[t] = 0 past the band
+          float vv[8];
+          bf16x8_to_f32(*reinterpret_cast<const int4*>(sV + j * hd + c * 64 + dl * 8), vv);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[c][k] = fmaf(p[t], vv[k], acc[c][k]);
         }
       }
     }
     if (valid) {
-      const float inv = 1.f / den;
+      const float inv = __fdividef(1.f, den);
       __nv_bfloat16* op = out + (static_cast<size_t>(sq) * N + i) * Hd + h * hd + dl * 8;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {

@@ -15,9 +15,10 @@ from . import fmt_oracle as O
 from . import refshim
 
 
-def make_cpu_sampler(W, dims, nfe, a_cfg, r_cfg, e_cfg, force_port=False):
-    """-> (kind, fn) with fn(r_s, wa, we, T, seed) -> r_d (B, T, dim_w) on the CPU, fp32, all host threads."""
-    torch.set_num_threads(os.cpu_count() or 1)
+def make_cpu_sampler(W, dims, nfe, a_cfg, r_cfg, e_cfg, force_port=False, threads=None):
+    """-> (kind, fn) with fn(r_s, wa, we, T, seed) -> r_d (B, T, dim_w) on the CPU, fp32, all host threads (or `threads` of them
+    when several processes share the host, one per rank)."""
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     if refshim.reference_available() and not force_port:
         _, model, _ = refshim.build_reference_fmt(W)
         node = importlib.import_module("refnodes.nodes_vadv").FloatSampleMotionSequenceRD_VA()
