@@ -339,48 +339,32 @@ def main():
 
     # ------------------------------------------------------------------ reference arm: the reference node on the host cores, rank 0 only
     if args.impl == "reference":
-        # One CPU process per rank, each on its share of the host cores and on its own clip(s) - the same data-parallel split as
-        # the product arm, so that the aggregate frames/s of the two arms compare like with like at every N.
+        if rank != 0:
+            return
         from oracle import ref_arm
-        dist = None
-        if world > 1:
-            import torch.distributed as dist
-            dist.init_process_group("gloo")
-            torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
         W = synth.synth_state_dict(dims, seed=0)
-        kind, run = ref_arm.make_cpu_sampler(W, dims, NFE, A_CFG, R_CFG, E_CFG, force_port=args.force_port,
-                                             threads=torch.get_num_threads() if world > 1 else None)
-        r_s, wa, we = workload_inputs(dims, B, T, rank)
+        kind, run = ref_arm.make_cpu_sampler(W, dims, NFE, A_CFG, R_CFG, E_CFG, force_port=args.force_port)
+        r_s, wa, we = workload_inputs(dims, B, T, 0)
         t0 = time.perf_counter()
         run(r_s, wa[:, :L], we, L, 15)
         t_win = time.perf_counter() - t0
         total = args.steps + args.warmup
-        fits = torch.tensor([1.0 if t_win * n_win * total <= 150 else 0.0])
-        if world > 1:
-            dist.all_reduce(fits, op=dist.ReduceOp.MIN)      # every rank times the same sample
-        frames = T if fits.item() > 0 else L
+        frames = T if t_win * n_win * total <= 150 else L
         sample = (f"whole workload per step ({B} clip x {T} frames)" if frames == T else
                   f"first window per step ({B} clip x {L} frames, {S} ODE steps)") + "; " + ref_arm.describe(kind)
         for _ in range(max(0, args.warmup - 1)):
             run(r_s, wa[:, :frames], we, frames, 15)
-        if world > 1:
-            dist.barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            run(r_s, wa[:, :frames], we, frames, 15 + rank)
-        el_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(el_t, op=dist.ReduceOp.MAX)      # the job is done when the slowest process is
-            dist.destroy_process_group()
-        if rank != 0:
-            return
-        el = float(el_t.item())
-        v = args.steps * world * B * frames / el
+            run(r_s, wa[:, :frames], we, frames, 15)
+        el = time.perf_counter() - t0
+        v = args.steps * B * frames / el
         print(json.dumps(dict(impl="reference", metric="motion-latent frames/s (FMT, nfe=10)", value=v, unit="frames/s", n_gpus=args.gpus,
                               steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * el / args.steps, higher_is_better=True, scaling="weak",
-                              vs_baseline=None, dtype="f32", data="synthetic", config=config, cpu_processes=world,
-                              cpu_baseline=dict(value=v, unit="frames/s", cores=torch.get_num_threads() * world, kind=kind,
-                                                sample=sample + (f"; {world} processes x {torch.get_num_threads()} threads, one per rank" if world > 1 else "")),
+                              vs_baseline=None, dtype="f32", data="synthetic", config=config, cpu_processes=1,
+                              note="ONE CPU process (rank 0, all host cores) on one GPU's share of the workload, whatever --gpus says: "
+                                   "compare it with the product arm's per-GPU value, not with its N-GPU aggregate",
+                              cpu_baseline=dict(value=v, unit="frames/s", cores=torch.get_num_threads(), kind=kind, sample=sample),
                               e2e=dict(value=v, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
         return
 
