@@ -2,7 +2,7 @@
 //   * gemm_tc_kernel   - bf16 operands, tcgen05.mma (cta_group::1, M=128 x N=BN x K=16) with fp32 accumulators in
 //                        TMEM, operands staged by TMA (128B swizzle) through an mbarrier ring; persistent over
 //                        output tiles with a double-buffered accumulator so the epilogue of tile i overlaps the
-//                        MMAs of tile i+1.  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue.
+//                        MMAs of tile i+1.  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..11 = epilogue.
 //   * gemm_simt_kernel - fp32 operands, plain FFMA tiles; FMT_MODE_FP32_VALIDATE only (the 1e-4 parity mode).
 // Both share epi_apply(), which carries the fused epilogues of the reference's block
 // (FMT.py:171-176): bias, GELU(tanh), +pos_embed, and x += gate * (.).
@@ -170,7 +170,8 @@ template <int BN> struct TcCfg {
   static constexpr int TMEM_COLS = ACC_STAGES * BN;     // 128 / 256 / 512: powers of two >= 32
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual 1 KB alignment for SWIZZLE_128B
-  static constexpr int THREADS = 192;
+  static constexpr int EPI_WARPS = 8;                    // warps 4..11: two per TMEM lane quarter, each takes every other 32-column chunk
+  static constexpr int THREADS = 128 + EPI_WARPS * 32;   // warpgroup 0 = TMA producer, MMA issuer, TMEM allocator, one idle warp
   static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
 };
 
@@ -198,7 +199,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < C::ACC_STAGES; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < C::ACC_STAGES; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], C::EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -211,6 +212,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
 
+  // register budget per warpgroup: the role warps need few registers, the fused epilogues many (residual + gate rows in flight).
+  // The setmaxnreg sits INSIDE each role branch: ptxas budgets a region that both branches reach with the smaller value.
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
@@ -258,23 +263,86 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     __syncwarp();
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ===================== epilogue warps (TMEM -> registers -> global) =====================
+    // Eight warps: with the fused epilogues (GELU, gate + residual) four warps - one per scheduler - took longer over a tile than
+    // the tensor pipe over its main loop, and the GEMM ran at the epilogue's pace (fc1 at 32 clips: 63 us in the step against
+    // 41 us with a plain store).  Two warps per lane quarter split the tile's column chunks.
     const int quarter = warp & 3;                          // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int half = (warp - 4) >> 2;                      // 0: even chunks, 1: odd chunks
     pdl_wait_prior_grid();
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int m0 = (t % m_tiles) * C::BM, n0 = (t / m_tiles) * BN;
       const int m = m0 + quarter * 32 + lane;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      if (ep.kind == EPI_GATE_RES) {
+        // x += gate * (acc + bias), FMT.py:174-175.  The residual and gate rows of this warp's first chunk are requested BEFORE the
+        // accumulator is waited for, those of its next chunk as soon as the current ones have been consumed: at K = 1024 a tile's
+        // main loop lasts ~1 us, loading the rows inside the chunk loop made the epilogue twice as long as that (proj at 32 clips:
+        // 22-33 us in the step against 17 us with a plain store).
+        const bool row_ok = m < ep.M;
+        const int mc = row_ok ? m : ep.M - 1;               // clamped row: loads stay in bounds, stores are predicated
+        float* xrow = reinterpret_cast<float*>(ep.out) + static_cast<size_t>(mc) * ep.ldo + n0;
+        const TT* grow = reinterpret_cast<const TT*>(ep.gate) + static_cast<size_t>(ep.urow ? ep.urow[mc] : mc) * ep.ldg + ep.gate_off + n0;
+        const float* brow = ep.bias != nullptr ? ep.bias + n0 : nullptr;
+        float4 xq[8], bq[8];
+        constexpr int GW = 32 * sizeof(TT) / 16;            // 16-byte words per 32 gate values
+        uint4 graw[GW];
+        auto prefetch = [&](int c) {
+          if (n0 + c * 32 < ep.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              xq[i] = *reinterpret_cast<const float4*>(xrow + c * 32 + i * 4);
+              bq[i] = brow != nullptr ? __ldg(reinterpret_cast<const float4*>(brow + c * 32 + i * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < GW; ++i) graw[i] = reinterpret_cast<const uint4*>(grow + c * 32)[i];
+          }
+        };
+        prefetch(half);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, v);
-        tmem_ld_wait();
-        const int n = n0 + c * 32;
-        if (m < ep.M && n < ep.N) epi_apply<__nv_bfloat16, TT, 32>(ep, m, n, v);
+        for (int c = half; c < BN / 32; c += 2) {
+          float v[32], g[32];
+          tmem_ld32(t_addr + c * 32, v);
+          tmem_ld_wait();
+          if constexpr (sizeof(TT) == 2) {
+#pragma unroll
+            for (int i = 0; i < GW; ++i) {
+              const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&graw[i]);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { g[8 * i + 2 * k] = __low2float(hp[k]); g[8 * i + 2 * k + 1] = __high2float(hp[k]); }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < GW; ++i) { g[4 * i] = __uint_as_float(graw[i].x); g[4 * i + 1] = __uint_as_float(graw[i].y); g[4 * i + 2] = __uint_as_float(graw[i].z); g[4 * i + 3] = __uint_as_float(graw[i].w); }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v[4 * i] = fmaf(g[4 * i], v[4 * i] + bq[i].x, xq[i].x);
+            v[4 * i + 1] = fmaf(g[4 * i + 1], v[4 * i + 1] + bq[i].y, xq[i].y);
+            v[4 * i + 2] = fmaf(g[4 * i + 2], v[4 * i + 2] + bq[i].z, xq[i].z);
+            v[4 * i + 3] = fmaf(g[4 * i + 3], v[4 * i + 3] + bq[i].w, xq[i].w);
+          }
+          const bool ok = row_ok && n0 + c * 32 < ep.N;
+          if (c + 2 < BN / 32) prefetch(c + 2);
+          if (ok) store_row32(xrow + c * 32, v);
+        }
+      } else {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += 2) {
+          float v[32];
+          tmem_ld32(t_addr + c * 32, v);
+          tmem_ld_wait();
+          const int n = n0 + c * 32;
+          if (m < ep.M && n < ep.N) epi_apply<__nv_bfloat16, TT, 32>(ep, m, n, v);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -294,7 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // 96 B/clk of operand reads + 96 B/clk of TMA fills against 128 B/clk).  Accumulators: 128 lanes x BN columns in EACH
 // CTA's TMEM, double buffered; each CTA's epilogue warps drain their own half.
 // Barriers: full (leader only, tx bytes of BOTH CTAs), empty / tmem-full (commit multicast to both CTAs),
-// tmem-empty (leader, 8 arrivals = 4 epilogue warps x 2 CTAs).
+// tmem-empty (leader, 16 arrivals = 8 epilogue warps x 2 CTAs).
 // ------------------------------------------------------------------------------------------------
 // Tile rasterisation: tiles are walked in groups of GM row-tiles x all column-tiles (row fastest inside a group), so the
 // ~74 tiles in flight at any time cover a GM x (74/GM) block: every A tile is shared by ~74/GM tiles and every B tile by GM
@@ -317,7 +385,8 @@ template <int BN> struct Tc2Cfg {
   static constexpr int TMEM_COLS = ACC_STAGES * BN;
   static constexpr int BAR_BYTES = 256 + BN * 4;        // barriers + tmem slot, then the tile's bias (BN floats)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
-  static constexpr int THREADS = 192;
+  static constexpr int EPI_WARPS = 8;                    // per CTA, warps 4..11: two per TMEM lane quarter, each takes every other 32-column chunk
+  static constexpr int THREADS = 128 + EPI_WARPS * 32;   // warpgroup 0 = TMA producer, MMA issuer, TMEM allocator, one idle warp
   static_assert(BN == 128 || BN == 256, "BN");
 };
 
@@ -348,7 +417,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < C::ACC_STAGES; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    for (int i = 0; i < C::ACC_STAGES; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * C::EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -362,6 +431,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ===================== TMA producer (both CTAs; bytes are counted on the leader's full barrier) =====================
     if (lane == 0) {
@@ -412,14 +483,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
     __syncwarp();
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ===================== epilogue warps: this CTA's 128 rows =====================
     // The epilogue of tile i runs under the MMAs of tile i+1, so it must stay shorter than one main loop (4.5 us at
     // K = 1024).  Everything it reads from global memory is therefore requested ahead of use: the tile's bias goes to smem
     // once, and the residual / gate / pos_embed operands of chunk c+1 are in flight while chunk c is computed (a first
     // version that loaded them inside the chunk loop took 12 us per tile and made the whole GEMM epilogue-bound).
+    // Eight epilogue warps per CTA, two per TMEM lane quarter (warp % 4), each taking every other 32-column chunk of the tile: with
+    // four - one per scheduler - the GELU and gate + residual epilogues took longer than the main loop and paced the GEMM.
     const int quarter = warp & 3;
-    const int et = threadIdx.x - 64;                        // 0..127 among the epilogue threads
+    const int half = (warp - 4) >> 2;                       // 0: even chunks, 1: odd chunks
+    constexpr int ET = C::EPI_WARPS * 32;
+    const int et = threadIdx.x - 128;                       // 0..ET-1 among the epilogue threads
     float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);   // BN floats behind the barriers
     pdl_wait_prior_grid();
     int acc = 0; uint32_t acc_phase = 0;
@@ -431,81 +508,101 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int m = m0 + quarter * 32 + lane;
       const bool row_ok = m < ep.M;
       const int mc = row_ok ? m : ep.M - 1;                 // clamped row: loads stay in bounds, stores are predicated
-      named_bar_sync(1, 128);                               // previous tile's readers of bias_s are done
-      for (int i = et; i < BN; i += 128) bias_s[i] = (ep.bias != nullptr && first_slice && n0 + i < ep.N) ? ep.bias[n0 + i] : 0.f;
-      named_bar_sync(1, 128);
+      named_bar_sync(1, ET);                                // previous tile's readers of bias_s are done
+      for (int i = et; i < BN; i += ET) bias_s[i] = (ep.bias != nullptr && first_slice && n0 + i < ep.N) ? ep.bias[n0 + i] : 0.f;
+      named_bar_sync(1, ET);
       constexpr int NCH = BN / 32;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
       if (ep.kind == EPI_GATE_RES) {
         float* xrow = reinterpret_cast<float*>(ep.out) + static_cast<size_t>(mc) * ep.ldo + n0;
         const TT* grow = reinterpret_cast<const TT*>(ep.gate) + static_cast<size_t>(ep.urow ? ep.urow[mc] : mc) * ep.ldg + ep.gate_off + n0;
-        float4 xq[2][8];
-        float gq[2][32];
-        auto prefetch = [&](int c, int b) {
+        // Software pipeline over this warp's chunks: the residual and gate rows of chunk c+2 are requested as soon as those of chunk
+        // c have been consumed (same registers), so they are in flight during the stores and the next TMEM load; the second warp of
+        // the lane quarter covers the rest of the latency.  The gate row stays in the table's type while it is in flight.
+        float4 xq[8];
+        constexpr int GW = 32 * sizeof(TT) / 16;                            // 16-byte words per 32 gate values
+        uint4 graw[GW];
+        auto prefetch = [&](int c) {
           if (n0 + c * 32 < ep.N) {
             if (ksplit == 1) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) xq[b][i] = *reinterpret_cast<const float4*>(xrow + c * 32 + i * 4);
+              for (int i = 0; i < 8; ++i) xq[i] = *reinterpret_cast<const float4*>(xrow + c * 32 + i * 4);
             }
-            VecIO<TT, 32>::load(grow + c * 32, gq[b]);
+#pragma unroll
+            for (int i = 0; i < GW; ++i) graw[i] = reinterpret_cast<const uint4*>(grow + c * 32)[i];
           }
         };
-        prefetch(0, 0);
+        prefetch(half);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          if (c + 1 < NCH) prefetch(c + 1, (c + 1) & 1);
+#pragma unroll 1
+        for (int c = half; c < NCH; c += 2) {
           float v[32];
           tmem_ld32(t_addr + c * 32, v);
           tmem_ld_wait();
-          if (row_ok && n0 + c * 32 < ep.N && ksplit > 1) {
-            // K-sliced tile: x += gate * partial, summed in L2 by fp32 RED (the order of the slices is not fixed)
+          const bool ok = row_ok && n0 + c * 32 < ep.N;
+          float g[32];
+          if constexpr (sizeof(TT) == 2) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              red_add_v4(xrow + c * 32 + i * 4, gq[c & 1][4 * i] * (v[4 * i] + bias_s[c * 32 + 4 * i]), gq[c & 1][4 * i + 1] * (v[4 * i + 1] + bias_s[c * 32 + 4 * i + 1]),
-                         gq[c & 1][4 * i + 2] * (v[4 * i + 2] + bias_s[c * 32 + 4 * i + 2]), gq[c & 1][4 * i + 3] * (v[4 * i + 3] + bias_s[c * 32 + 4 * i + 3]));
-          } else if (row_ok && n0 + c * 32 < ep.N) {
-            float o[32];
+            for (int i = 0; i < GW; ++i) {
+              const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&graw[i]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {                                   // x = x + gate * branch  (FMT.py:174-175)
-              const float4 x = xq[c & 1][i];
-              o[4 * i] = fmaf(gq[c & 1][4 * i], v[4 * i] + bias_s[c * 32 + 4 * i], x.x);
-              o[4 * i + 1] = fmaf(gq[c & 1][4 * i + 1], v[4 * i + 1] + bias_s[c * 32 + 4 * i + 1], x.y);
-              o[4 * i + 2] = fmaf(gq[c & 1][4 * i + 2], v[4 * i + 2] + bias_s[c * 32 + 4 * i + 2], x.z);
-              o[4 * i + 3] = fmaf(gq[c & 1][4 * i + 3], v[4 * i + 3] + bias_s[c * 32 + 4 * i + 3], x.w);
+              for (int k = 0; k < 4; ++k) { g[8 * i + 2 * k] = __low2float(hp[k]); g[8 * i + 2 * k + 1] = __high2float(hp[k]); }
             }
-            store_row32(xrow + c * 32, o);
+          } else {
+#pragma unroll
+            for (int i = 0; i < GW; ++i) { g[4 * i] = __uint_as_float(graw[i].x); g[4 * i + 1] = __uint_as_float(graw[i].y); g[4 * i + 2] = __uint_as_float(graw[i].z); g[4 * i + 3] = __uint_as_float(graw[i].w); }
+          }
+          if (ksplit > 1) {
+            // K-sliced tile: x += gate * partial, summed in L2 by fp32 RED (the order of the slices is not fixed)
+            if (c + 2 < NCH) prefetch(c + 2);
+            if (ok) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                red_add_v4(xrow + c * 32 + i * 4, g[4 * i] * (v[4 * i] + bias_s[c * 32 + 4 * i]), g[4 * i + 1] * (v[4 * i + 1] + bias_s[c * 32 + 4 * i + 1]),
+                           g[4 * i + 2] * (v[4 * i + 2] + bias_s[c * 32 + 4 * i + 2]), g[4 * i + 3] * (v[4 * i + 3] + bias_s[c * 32 + 4 * i + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {                                   // x = x + gate * branch  (FMT.py:174-175), in place
+              const float4 x = xq[i];
+              v[4 * i] = fmaf(g[4 * i], v[4 * i] + bias_s[c * 32 + 4 * i], x.x);
+              v[4 * i + 1] = fmaf(g[4 * i + 1], v[4 * i + 1] + bias_s[c * 32 + 4 * i + 1], x.y);
+              v[4 * i + 2] = fmaf(g[4 * i + 2], v[4 * i + 2] + bias_s[c * 32 + 4 * i + 2], x.z);
+              v[4 * i + 3] = fmaf(g[4 * i + 3], v[4 * i + 3] + bias_s[c * 32 + 4 * i + 3], x.w);
+            }
+            if (c + 2 < NCH) prefetch(c + 2);                               // the rows of this warp's next chunk, into the registers just consumed
+            if (ok) store_row32(xrow + c * 32, v);
           }
         }
       } else {
         const float* prow = ep.kind == EPI_POS ? ep.pos + static_cast<size_t>(mc % ep.frames) * ep.N + n0 : nullptr;
-        float4 pq[2][8];
-        auto prefetch = [&](int c, int b) {
+        float4 pq[8];
+        auto prefetch = [&](int c) {
           if (prow != nullptr && n0 + c * 32 < ep.N) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) pq[b][i] = *reinterpret_cast<const float4*>(prow + c * 32 + i * 4);
+            for (int i = 0; i < 8; ++i) pq[i] = *reinterpret_cast<const float4*>(prow + c * 32 + i * 4);
           }
         };
-        prefetch(0, 0);
+        prefetch(half);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          if (c + 1 < NCH) prefetch(c + 1, (c + 1) & 1);
+#pragma unroll 1
+        for (int c = half; c < NCH; c += 2) {
           float v[32];
           tmem_ld32(t_addr + c * 32, v);
           tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += bias_s[c * 32 + i];
+          if (ep.kind == EPI_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_approx(v[i]);   // tanh.approx: 2^-11, below the bf16 rounding of the output
+          } else if (ep.kind == EPI_POS) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[4 * i] += pq[i].x; v[4 * i + 1] += pq[i].y; v[4 * i + 2] += pq[i].z; v[4 * i + 3] += pq[i].w; }
+            if (c + 2 < NCH) prefetch(c + 2);
+          }
           if (row_ok && n0 + c * 32 < ep.N) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += bias_s[c * 32 + i];
-            if (ep.kind == EPI_GELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_approx(v[i]);   // tanh.approx: 2^-11, below the bf16 rounding of the output
-            } else if (ep.kind == EPI_POS) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { v[4 * i] += pq[c & 1][i].x; v[4 * i + 1] += pq[c & 1][i].y; v[4 * i + 2] += pq[c & 1][i].z; v[4 * i + 3] += pq[c & 1][i].w; }
-            }
             if (ep.out_f32) store_row32(reinterpret_cast<float*>(ep.out) + static_cast<size_t>(m) * ep.ldo + n0 + c * 32, v);
             else store_row32(reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(m) * ep.ldo + n0 + c * 32, v);
           }
