@@ -344,7 +344,7 @@ static int launch_attn(FmtHandle* h, cudaStream_t st) {
   const int win = h->d.attention_window;
   if constexpr (sizeof(T) == 2) {
     // many sequences: one CTA per (sequence, head) with K / V staged in shared memory (every qkv byte read once)
-    const size_t tile_smem = static_cast<size_t>(3) * s.N * hd * sizeof(bf16);   // Q, K, V of one (sequence, head)
+    const size_t tile_smem = static_cast<size_t>(2) * s.N * hd * sizeof(bf16);   // K, V of one (sequence, head)
     if (n_seq * heads >= 2 * h->num_sms && tile_smem <= 48 * 1024 && (hd == 64 || hd == 128)) {
       const bf16* q16 = reinterpret_cast<const bf16*>(qkv);
       bf16* o16 = reinterpret_cast<bf16*>(out);
