@@ -100,7 +100,7 @@ struct FmtHandle {
   int flow_max_rows = 256;                       // plans with more token rows run one kernel per op (FMT_FLOW_MAX_ROWS)
   int flow_fixed = 14;                           // FMT_FLOW_FIXED: split-K partial sums are rounded to multiples of 2^-k before they meet in L2 (exact, order-independent sums below 2^(24-k): bitwise reproducible runs); 0 = off
   int flow_poll = 1;                             // FMT_FLOW_POLL: 0 = acquire polls, 1 = relaxed polls + one acquire load
-  long long flow_spin_limit = 4000000000ll;      // SM clocks a wait may spin before the kernel traps (FMT_FLOW_SPIN_MS)
+  long long flow_spin_limit = 20000000000ll;     // SM clocks (~10 s) a wait may spin before the kernel traps (FMT_FLOW_SPIN_MS): long enough to survive a time-sliced GPU, short enough to end a protocol bug
   FlowParams flow_params{};
   DevBuf flow_gemms, flow_tmaps, flow_acc, flow_act, flow_flags, flow_trace;
   bool win_grouped = false;                      // the active plan runs fmt_window_kernel<NV, true>
