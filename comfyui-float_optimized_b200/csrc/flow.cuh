@@ -241,6 +241,7 @@ __device__ __forceinline__ void flow_mma_issuer(const FlowParams& p, const FlowI
       for (int c = 0; c < nc; ++c) {
         flow_mbar_wait(p, &sm.t_empty[t_slot], t_phase ^ 1, 0x04000000 | (e << 16) | (g << 8) | c);
         flow_mbar_wait(p, &sm.a_full[a_slot], a_phase, 0x05000000 | (e << 16) | (g << 8) | c);
+        if (leader) flow_mark(p, e, 0, g, c, 7);                         // trace: the activation tile has landed
         int ws = w_slot; uint32_t wp = w_phase;
         const uint32_t d_addr = tmem_base + static_cast<uint32_t>(t_slot * CH);
         const bool last_chunk = c == nc - 1;

@@ -91,6 +91,12 @@ with np.errstate(all="ignore"):
     print("\nGEMM engine per (stage, chunk), mean over CTAs with an item: loader wait for the flag %.2f | for a ring slot %.2f | load+MMA (slot -> acc) %.2f | "
           "acc -> reduce issued %.2f | issued -> published %.2f" % (np.nanmean(G[..., 1] - G[..., 0]), np.nanmean(G[..., 2] - G[..., 1]), np.nanmean(G[..., 3] - G[..., 2]),
                                                                    np.nanmean(G[..., 4] - G[..., 3]), np.nanmean(G[..., 5] - G[..., 4])))
+    print("  GEMM front end: copy issued -> tile landed (seen by the MMA warp) %.2f | landed -> accumulator ready (seen by the epilogue) %.2f" % (
+        np.nanmean(G[..., 7] - G[..., 2]), np.nanmean(G[..., 3] - G[..., 7])))
+    for j_, nm_ in enumerate(("qkv", "proj", "fc1", "fc2")):
+        Gj = G[:, j_::4]
+        print("    %-4s: issued -> landed %.2f | landed -> acc ready %.2f | acc -> reduce issued %.2f | issued -> published %.2f" % (
+            nm_, np.nanmean(Gj[..., 7] - Gj[..., 2]), np.nanmean(Gj[..., 3] - Gj[..., 7]), np.nanmean(Gj[..., 4] - Gj[..., 3]), np.nanmean(Gj[..., 5] - Gj[..., 4])))
     print("SIMT engine per (stage, chunk) with units: wait %.2f | work %.2f | fence+bar %.2f | release %.2f" % (
         np.nanmean(S[..., 1] - S[..., 0]), np.nanmean(S[..., 2] - S[..., 1]), np.nanmean(S[..., 3] - S[..., 2]), np.nanmean(S[..., 4] - S[..., 3])))
     for kind, sl in (("attn", slice(0, None, 4)), ("row", slice(1, None, 4)), ("gelu", slice(2, None, 4)), ("row2", slice(3, None, 4))):
