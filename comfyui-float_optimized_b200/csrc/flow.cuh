@@ -10,12 +10,17 @@
 //     split-K GEMM of a chunk starts as soon as the SIMT stage before it has finished THAT chunk, the SIMT stage of a chunk as
 //     soon as every K slice of THAT chunk has been reduced.  Nothing is ever reset: counters are per instance.
 //   * A CTA is two engines that walk the same stage list independently.  GEMM engine: warp 0 streams this CTA's weight tiles
-//     of all stages through an 8-slot ring (free-running, HBM -> smem), warp 1 fetches the activation tile of each (item, chunk)
+//     of all stages through a ring of 7-8 slots (free-running, HBM -> smem), warp 1 fetches the activation tile of each (item, chunk)
 //     once its counter is complete, warp 2 issues tcgen05.mma (weights = A operand, M = 128; the chunk's rows = B operand,
 //     N = CH; fp32 accumulator in a ring of TMEM column slots), warps 4-7 drain TMEM -> smem -> L2 with TMA reduce-add and
 //     publish the chunk.  SIMT engine: warps 8-15 run the row-wise stages (bias / gate / residual / LayerNorm / AdaLN
 //     modulate, band attention, GELU, CFG combine + ODE update) on the units of each (stage, chunk) dealt to this CTA.
-//     The weight tiles of an item stay in shared memory while all chunks pass over them.
+//     The weight tiles of an item stay in shared memory while all chunks pass over them.  The row-wise units of a chunk run on
+//     that chunk's own slice of the grid, so the in-order SIMT engine of a CTA serves one chain.
+//   * The K slices of a tile meet in L2 through fp32 reduce-adds of partial sums rounded to a common quantum: exact, hence
+//     order-independent sums - the same seed gives the same bits on every run (flow_quantize).
+//
+// What bounds a step (34 GEMM + row-wise stage pairs of ~9 us per evaluation) and every measured dead end: DESIGN.md section 6.
 //
 // Reference semantics: FMT.py:151-198 (block / decoder), :277-340 (forward), :342-401 (CFG), torchdiffeq fixed-grid solvers.
 #pragma once
