@@ -70,7 +70,13 @@ def algorithmic_work(dims, B, nb, S):
     macs_row = step_params + NT * H + H * Kc                                    # every Linear, per token row (hoisting moves, not removes)
     attn_flops_row = 4 * N * H                                                  # dense-equivalent QK^T + PV, as the reference computes
     flops_step = rows * (2 * macs_row + attn_flops_row)
-    return dict(step_bytes=step_bytes, window_bytes=S * step_bytes + prep_bytes, window_flops=S * flops_step, rows=rows)
+    # What the product executes: the AdaLN projections run once per DISTINCT condition row (the unconditional branch's current frames
+    # share one row per clip and its context rows equal the audio-only branch's: 2N + 1 of 3N rows with 3-way CFG), everything else per
+    # token row.  Reported beside the algorithmic (reference-equivalent) count, which is what the roofline fraction is defined on.
+    distinct = B * (2 * N + 1) if nb == 3 and os.environ.get("FMT_DEDUP", "1") != "0" else rows
+    flops_step_exec = rows * (2 * step_params + attn_flops_row) + distinct * 2 * (NT * H + H * Kc)
+    return dict(step_bytes=step_bytes, window_bytes=S * step_bytes + prep_bytes, window_flops=S * flops_step, rows=rows,
+                window_flops_executed=S * flops_step_exec, distinct_condition_rows=distinct)
 
 
 class ClockSampler:
@@ -305,7 +311,9 @@ def roofline_record(dims, B, T, t_step, n_win, pk):
     roof.update(peak_source=pk["source"], launch="one captured window graph = prepare + %d ODE steps" % S, dominant_kernel=prof.get("kernel"),
                 traffic_source=prof.get("source"),
                 us_per_ode_step=1e6 * t_window / S, algorithmic_bytes_per_window=work["window_bytes"],
-                algorithmic_flops_per_window=work["window_flops"], other_bound_frac=min(hbm_frac, tf_frac))
+                algorithmic_flops_per_window=work["window_flops"], other_bound_frac=min(hbm_frac, tf_frac),
+                executed_flops_per_window=work["window_flops_executed"], distinct_condition_rows=work["distinct_condition_rows"],
+                token_rows=work["rows"], executed_tflops=work["window_flops_executed"] / t_window / 1e12)
     return roof
 
 

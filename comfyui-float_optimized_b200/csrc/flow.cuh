@@ -61,7 +61,9 @@ struct FlowParams {
   const CUtensorMap* tmaps;
   float *X, *Pacc, *QKVacc, *Hacc, *Vacc;          // padded rows; QKVacc holds two buffers (block parity)
   __nv_bfloat16 *A1, *A2, *Hm, *ax;                // A1 / A2 / Hm: [chunk][K block][CH][64] bf16, 128-byte swizzle applied
-  const __nv_bfloat16* table;                      // (n_eval, R, NT)
+  const __nv_bfloat16* table;                      // (n_eval, U, NT): one row per DISTINCT condition row
+  const int* urow;                                 // table row of every token row (nullptr: identity, U = R)
+  int U;
   const float *b_x, *pos, *b_dec;
   const float *b_qkv[WIN_MAX_DEPTH], *b_proj[WIN_MAX_DEPTH], *b_fc1[WIN_MAX_DEPTH], *b_fc2[WIN_MAX_DEPTH];
   float *x_state, *kbuf;
@@ -409,7 +411,8 @@ __device__ __forceinline__ void flow_row_units(const FlowParams& p, const FlowCh
     const size_t prow = static_cast<size_t>(ck.rp0 + (valid ? r : 0));
     float* acc = p.Pacc + prow * H + c0;
     float* xr = p.X + prow * H + c0;
-    const __nv_bfloat16* trow = table_e + static_cast<size_t>(ck.rr0 + (valid ? r : 0)) * p.NT + c0;
+    const int trow_i = ck.rr0 + (valid ? r : 0);
+    const __nv_bfloat16* trow = table_e + static_cast<size_t>(p.urow != nullptr ? __ldg(p.urow + trow_i) : trow_i) * p.NT + c0;
     float4 a[FPL], x[FPL], b[FPL], ps[FPL];
     uint2 tg[FPL], tsh[FPL], tsc[FPL];
     // unconditional (row 0 stands in for a row past the chunk): conditionally defined registers would be demoted to local memory
@@ -745,7 +748,7 @@ __device__ __forceinline__ void flow_simt_engine(const FlowParams& p, const Flow
   const size_t qkv_buf = static_cast<size_t>(p.RP) * 3 * H;
   const int hd = p.s.H / p.heads;
   for (int e = 0; e < n_eval; ++e) {
-    const __nv_bfloat16* table_e = p.table + static_cast<size_t>(e) * (static_cast<size_t>(p.R) * p.NT);
+    const __nv_bfloat16* table_e = p.table + static_cast<size_t>(e) * (static_cast<size_t>(p.U) * p.NT);
     for (int si = 0; si < n_st; ++si) {
       const int kind = flow_simt_kind(p, si);
       const int blk = (si >= 1 && si < n_st - 1) ? (si - 1) >> 2 : 0;

@@ -9,6 +9,8 @@
 #include "flow.cuh"
 
 #include <algorithm>
+#include <map>
+#include <tuple>
 #include <cstdlib>
 
 #include <cstdarg>
@@ -84,6 +86,9 @@ struct FmtHandle {
 
   // workspace
   DevBuf cond, cemb, temb, tfreq, th, silu, table, xstate, ystage, kbuf, prevx, ax, X, A1, QKV, A2, Hm, V, ddt, dteval, wargs;
+  DevBuf urow_buf, uidx_buf;                     // condition-row deduplication: table row of every token row / token row each table row stands for
+  bool dedup = false;                            // U < R: the AdaLN tables hold one row per DISTINCT condition row (FMT_DEDUP=0 switches it off)
+  int use_dedup = 1;
   DevBuf st_rs, st_wa, st_we, st_noise, st_rd;   // staging for host-located clips
   bool use_splitk = false;                       // 2-way K slicing of gate+residual GEMMs with a ragged last wave (FMT_SPLITK=1; measured 3 % slower at 32 clips)
   int raster_gm = 8;                             // FMT_RASTER_GM
@@ -296,7 +301,8 @@ template <typename T>
 static int enqueue_prepare(FmtHandle* h, cudaStream_t st) {
   const ModelShape& s = h->shape;
   const WindowArgs* wa = static_cast<const WindowArgs*>(h->wargs.p);
-  FMT_OK(launch(h, cond_gather_kernel<T>, dim3(h->U), dim3(128), 0, st, 1, wa, s, static_cast<T*>(h->cond.p)));
+  FMT_OK(launch(h, cond_gather_kernel<T>, dim3(h->U), dim3(128), 0, st, 1, wa, s, h->dedup ? static_cast<const int*>(h->uidx_buf.p) : nullptr,
+                static_cast<T*>(h->cond.p)));
   EpiParams ep = epi(EPI_STORE, h->U, s.H, h->c_emb.b, h->cemb.p, s.H, 1);
   FMT_OK(ModeOps<T>::gemm(h, h->cond.p, s.Kc, h->c_emb, ep, st));
   return 0;
@@ -321,7 +327,7 @@ static int launch_lnmod(FmtHandle* h, const T* table_e, long long shift_off, lon
   const dim3 grid((h->R + warps - 1) / warps), block(warps * 32);
   const float* X = static_cast<const float*>(h->X.p);
   T* out = static_cast<T*>(h->A1.p);
-  const int* urow = nullptr;
+  const int* urow = h->dedup ? static_cast<const int*>(h->urow_buf.p) : nullptr;
   const long long ldt = h->NT;
   switch (s.H / 128) {
     case 1: return launch(h, lnmod_kernel<T, T, 1>, grid, block, 0, st, 1, X, h->R, s.H, table_e, urow, ldt, shift_off, scale_off, out);
@@ -381,14 +387,14 @@ static int enqueue_forward(FmtHandle* h, int table_slot, cudaStream_t st) {
     FMT_OK(launch_attn<T>(h, st));
     {
       EpiParams ep = epi(EPI_GATE_RES, R, H, h->proj[i].b, h->X.p, H, 1);
-      ep.gate = table_e; ep.urow = nullptr; ep.ldg = h->NT; ep.gate_off = base + 2 * H;
+      ep.gate = table_e; ep.urow = h->dedup ? static_cast<const int*>(h->urow_buf.p) : nullptr; ep.ldg = h->NT; ep.gate_off = base + 2 * H;
       FMT_OK(ModeOps<T>::gemm(h, h->A2.p, H, h->proj[i], ep, st));
     }
     FMT_OK(launch_lnmod<T>(h, table_e, base + 3 * H, base + 4 * H, st));
     FMT_OK(ModeOps<T>::gemm(h, h->A1.p, H, h->fc1[i], epi(EPI_GELU, R, d.mlp_hidden, h->fc1[i].b, h->Hm.p, d.mlp_hidden, 0), st));
     {
       EpiParams ep = epi(EPI_GATE_RES, R, H, h->fc2[i].b, h->X.p, H, 1);
-      ep.gate = table_e; ep.urow = nullptr; ep.ldg = h->NT; ep.gate_off = base + 5 * H;
+      ep.gate = table_e; ep.urow = h->dedup ? static_cast<const int*>(h->urow_buf.p) : nullptr; ep.ldg = h->NT; ep.gate_off = base + 5 * H;
       FMT_OK(ModeOps<T>::gemm(h, h->Hm.p, d.mlp_hidden, h->fc2[i], ep, st));
     }
   }
@@ -638,6 +644,7 @@ static int setup_flow(FmtHandle* h, cudaStream_t st) {
   CUDA_OK(cudaMemsetAsync(h->flow_act.p, 0, h->flow_act.bytes, st));
   fp.A1 = static_cast<bf16*>(h->flow_act.p); fp.A2 = fp.A1 + t_a1; fp.Hm = fp.A2 + t_a1; fp.ax = static_cast<bf16*>(h->ax.p);
   fp.table = static_cast<const bf16*>(h->table.p);
+  fp.U = h->U; fp.urow = h->dedup ? static_cast<const int*>(h->urow_buf.p) : nullptr;
   fp.b_x = h->x_emb.b; fp.pos = h->pos; fp.b_dec = h->dec.b;
   for (int i = 0; i < D; ++i) { fp.b_qkv[i] = h->qkv[i].b; fp.b_proj[i] = h->proj[i].b; fp.b_fc1[i] = h->fc1[i].b; fp.b_fc2[i] = h->fc2[i].b; }
   fp.x_state = static_cast<float*>(h->xstate.p); fp.kbuf = static_cast<float*>(h->kbuf.p); fp.ddt = static_cast<const float*>(h->ddt.p);
@@ -910,6 +917,7 @@ int32_t fmt_create(const FmtDims* dims, const void* const* wp, int32_t n_ptrs, i
   if (const char* e = getenv("FMT_FLOW_CH")) { const int v = atoi(e); if (v == 32 || v == 64) h->flow_ch = v; }
   if (const char* e = getenv("FMT_FLOW_MAX_ROWS")) h->flow_max_rows = atoi(e);
   if (const char* e = getenv("FMT_FLOW_POLL")) h->flow_poll = atoi(e);
+  if (const char* e = getenv("FMT_DEDUP")) h->use_dedup = atoi(e) != 0;
   if (const char* e = getenv("FMT_FLOW_FIXED")) { const int v = atoi(e); if (v >= 0 && v <= 22) h->flow_fixed = v; }
   if (const char* e = getenv("FMT_FLOW_SPIN_MS")) h->flow_spin_limit = static_cast<long long>(atof(e) * 1.9e6);
   if (const char* e = getenv("FMT_WIN_SPG")) h->win_spg = atoi(e);
@@ -994,7 +1002,7 @@ int32_t fmt_destroy(FmtHandle* h) {
   DevBuf* bufs[] = {&h->cond, &h->cemb, &h->temb, &h->tfreq, &h->th, &h->silu, &h->table, &h->xstate, &h->ystage, &h->kbuf, &h->prevx, &h->ax,
                     &h->X, &h->A1, &h->QKV, &h->A2, &h->Hm, &h->V, &h->ddt, &h->dteval, &h->wargs, &h->st_rs, &h->st_wa, &h->st_we, &h->st_noise, &h->st_rd,
                     &h->win_params, &h->win_tmaps, &h->win_acc, &h->win_bar, &h->win_trace, &h->win_act,
-                    &h->flow_gemms, &h->flow_tmaps, &h->flow_acc, &h->flow_act, &h->flow_flags, &h->flow_trace};
+                    &h->flow_gemms, &h->flow_tmaps, &h->flow_acc, &h->flow_act, &h->flow_flags, &h->flow_trace, &h->urow_buf, &h->uidx_buf};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->win_err_host) cudaFreeHost(h->win_err_host);
@@ -1076,6 +1084,41 @@ int32_t fmt_configure(FmtHandle* h, const FmtPlan* p, void* stream) {
   else { s.null_a = s.null_r = s.null_e = 0; }
   h->R = s.nb * s.B * s.N;
   h->U = h->R;
+  // Distinct condition rows.  The CFG branches null whole inputs (FMT.py:360-392): the unconditional branch's current frames all see
+  // [wr | 0 | 0] - ONE condition row per clip instead of L - and its context frames see [wr | prev_wa | 0], the same rows as the
+  // audio-only branch's context frames (prev_wa is never nulled, prev_we is nulled like we).  c_embedder, SiLU and the AdaLN table
+  // GEMM only depend on the condition row and the evaluation, so they run on the U distinct rows (121 of 180 per clip with 3-way
+  // CFG) and every consumer of a table row goes through urow[].  Round 1's window kernels index the table by token row: plans that
+  // could fall back to them keep U = R.
+  h->dedup = false;
+  {
+    const bool old_window_plan = h->use_window != 0 && window_eligible(h, p) && !(h->use_window == 3 && flow_eligible(h, p));
+    if (h->use_dedup && s.nb > 1 && !old_window_plan) {
+      std::vector<int> urow(h->R), uidx;
+      std::map<std::tuple<int, int, int, int, int, int, int>, int> seen;
+      for (int row = 0; row < h->R; ++row) {
+        const int br = row / (s.B * s.N), b = (row / s.N) % s.B, f = row % s.N;
+        const bool za = (s.null_a >> br) & 1, zr = (s.null_r >> br) & 1, ze = (s.null_e >> br) & 1, ctx = f < s.P;
+        // what cond_gather_kernel reads for this row: (wr source, wa kind, wa clip, wa frame, we kind, we clip, we frame)
+        const int kr = zr ? -1 : b;
+        const int ka = ctx ? 0 : (za ? 1 : 2), kab = (ctx || !za) ? b : -1, kaf = (ctx || !za) ? f : -1;
+        const int ke = ze ? 0 : (s.we_dynamic ? 2 : 1), keb = ze ? -1 : b, kef = (!ze && s.we_dynamic) ? f : -1;
+        const auto key = std::make_tuple(kr, ka, kab, kaf, ke, keb, kef);
+        auto it = seen.find(key);
+        if (it == seen.end()) { it = seen.emplace(key, static_cast<int>(uidx.size())).first; uidx.push_back(row); }
+        urow[row] = it->second;
+      }
+      if (static_cast<int>(uidx.size()) < h->R) {
+        h->U = static_cast<int>(uidx.size());
+        h->dedup = true;
+        FMT_OK(dev_alloc(h, h->urow_buf, urow.size() * sizeof(int)));
+        FMT_OK(dev_alloc(h, h->uidx_buf, uidx.size() * sizeof(int)));
+        CUDA_OK(cudaMemcpyAsync(h->urow_buf.p, urow.data(), urow.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(h->uidx_buf.p, uidx.data(), uidx.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaStreamSynchronize(st));      // `urow` / `uidx` are stack objects
+      }
+    }
+  }
   const size_t ts = p->mode == FMT_MODE_BF16 ? 2 : 4;
   h->tsize = ts;
   const size_t R = h->R, U = h->U, H = s.H;
@@ -1142,7 +1185,7 @@ int32_t fmt_configure(FmtHandle* h, const FmtPlan* p, void* stream) {
     if (setup_flow(h, st) == 0 && launch_flow(h, st, /*probe_only=*/true) == 0) h->flow_active = true;
     else (void)cudaGetLastError();
   }
-  h->window_active = h->flow_active || (window_eligible(h, p) && h->table_chunk == ne);
+  h->window_active = h->flow_active || (window_eligible(h, p) && h->table_chunk == ne && !h->dedup);   // round 1's kernels index the table by token row
   if (h->window_active && !h->flow_active) {
     // the persistent kernel synchronises across the grid: it needs one resident CTA on every SM, else the plan runs one kernel per op
     int occ = 0;

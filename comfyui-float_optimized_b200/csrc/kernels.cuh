@@ -42,19 +42,20 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 // Condition rows  [wr | wa | we | 0-pad]  for every (branch, clip, frame)   (FMT.py:312-333, nodes_adv.py:609-627,663-686)
 // ---------------------------------------------------------------------------------------------------------------
 template <typename AT>
-__global__ void cond_gather_kernel(const WindowArgs* __restrict__ wargs, ModelShape s, AT* __restrict__ cond) {
+__global__ void cond_gather_kernel(const WindowArgs* __restrict__ wargs, ModelShape s, const int* __restrict__ uidx, AT* __restrict__ cond) {
   pdl_launch_dependents();
   pdl_wait_prior_grid();
   const WindowArgs a = *wargs;
   const int rows = s.nb * s.B * s.N;
-  const int row = blockIdx.x;
+  // uidx != nullptr: block u builds the u-th DISTINCT condition row, the one token row uidx[u] sees (fmt_configure)
+  const int row = uidx != nullptr ? uidx[blockIdx.x] : blockIdx.x;
   if (row >= rows) return;
   const int br = row / (s.B * s.N), b = (row / s.N) % s.B, f = row % s.N;
   const bool za = (s.null_a >> br) & 1, zr = (s.null_r >> br) & 1, ze = (s.null_e >> br) & 1;
   const bool ctx = f < s.P;
   // frame of the clip this row looks at; replicate padding == clamp to the last available frame
   const int g = a.win_start + f - s.P;
-  AT* out = cond + static_cast<size_t>(row) * s.Kc;
+  AT* out = cond + static_cast<size_t>(blockIdx.x) * s.Kc;
   for (int j = threadIdx.x; j < s.Kc; j += blockDim.x) {
     float v = 0.f;
     if (j < s.W) {
