@@ -66,6 +66,7 @@ _SIGNATURES = {
     "fmt_graph_kernel_nodes": (C.c_int32, [C.c_void_p]),
     "fmt_window_kernel_status": (C.c_int32, [C.c_void_p]),
     "fmt_debug_window_trace": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "fmt_debug_condition_rows": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "fmt_proj_create": (C.c_int32, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32,
                                     C.POINTER(C.c_void_p)]),
     "fmt_proj_destroy": (C.c_int32, [C.c_void_p]),

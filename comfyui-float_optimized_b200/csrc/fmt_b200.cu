@@ -1039,6 +1039,47 @@ int32_t fmt_window_kernel_status(const FmtHandle* h) {
   return h->win_err_host ? *h->win_err_host : 0;
 }
 
+// Which token rows (branch, clip, frame) see the same condition row [wr | wa | we]?  urow[row] = index of the row's distinct
+// condition row, uidx[u] = the first token row that sees distinct row u.  The key is exactly what cond_gather_kernel reads for a
+// row: the identity latent unless nulled (per clip), the audio latent (context frames read prev_wa, never nulled, FMT.py:366,388;
+// current frames read wa unless nulled), the emotion (nulled; static = per clip, covering the context frames too, FMT.py:325-326;
+// dynamic = per frame).
+static void distinct_condition_rows(const ModelShape& s, std::vector<int>& urow, std::vector<int>& uidx) {
+  const int R = s.nb * s.B * s.N;
+  urow.assign(R, 0);
+  uidx.clear();
+  std::map<std::tuple<int, int, int, int, int, int, int>, int> seen;
+  for (int row = 0; row < R; ++row) {
+    const int br = row / (s.B * s.N), b = (row / s.N) % s.B, f = row % s.N;
+    const bool za = (s.null_a >> br) & 1, zr = (s.null_r >> br) & 1, ze = (s.null_e >> br) & 1, ctx = f < s.P;
+    const int kr = zr ? -1 : b;
+    const int ka = ctx ? 0 : (za ? 1 : 2), kab = (ctx || !za) ? b : -1, kaf = (ctx || !za) ? f : -1;
+    const int ke = ze ? 0 : (s.we_dynamic ? 2 : 1), keb = ze ? -1 : b, kef = (!ze && s.we_dynamic) ? f : -1;
+    const auto key = std::make_tuple(kr, ka, kab, kaf, ke, keb, kef);
+    auto it = seen.find(key);
+    if (it == seen.end()) { it = seen.emplace(key, static_cast<int>(uidx.size())).first; uidx.push_back(row); }
+    urow[row] = it->second;
+  }
+}
+
+static void branch_nulls(ModelShape& s) {
+  if (s.nb == 3) { s.null_a = 0b001; s.null_r = 0; s.null_e = 0b101; }            // [uncond | all | audio-only]   FMT.py:360-362
+  else if (s.nb == 4) { s.null_a = 0b0011; s.null_r = 0b0001; s.null_e = 0b1011; } // [truly-uncond | uncond | all | audio-only] :382-384
+  else { s.null_a = s.null_r = s.null_e = 0; }
+}
+
+// Host-only view of the deduplication for tests (no device work): fills urow[n_branches * batch * n_frames], returns U.
+int32_t fmt_debug_condition_rows(int32_t n_branches, int32_t batch, int32_t n_frames, int32_t n_prev, int32_t we_dynamic, int32_t* urow_out) {
+  if (n_branches < 1 || n_branches > 4 || batch < 1 || n_frames < 1 || n_prev < 0 || n_prev > n_frames) return -1;
+  ModelShape s{};
+  s.nb = n_branches; s.B = batch; s.N = n_frames; s.P = n_prev; s.we_dynamic = we_dynamic;
+  branch_nulls(s);
+  std::vector<int> urow, uidx;
+  distinct_condition_rows(s, urow, uidx);
+  if (urow_out != nullptr) std::copy(urow.begin(), urow.end(), urow_out);
+  return static_cast<int32_t>(uidx.size());
+}
+
 static bool same_plan(const FmtHandle* h, const FmtPlan* p) {
   if (!h->configured) return false;
   const FmtPlan& q = h->plan;
@@ -1079,9 +1120,7 @@ int32_t fmt_configure(FmtHandle* h, const FmtPlan* p, void* stream) {
   ModelShape& s = h->shape;
   s.B = p->batch; s.nb = p->n_branches; s.N = h->N; s.P = d.num_prev_frames; s.L = d.frames_per_clip;
   s.W = d.dim_w; s.A = d.dim_a; s.E = d.dim_e; s.H = d.dim_h; s.Kc = h->Kc; s.we_dynamic = p->we_dynamic;
-  if (s.nb == 3) { s.null_a = 0b001; s.null_r = 0; s.null_e = 0b101; }            // [uncond | all | audio-only]   FMT.py:360-362
-  else if (s.nb == 4) { s.null_a = 0b0011; s.null_r = 0b0001; s.null_e = 0b1011; } // [truly-uncond | uncond | all | audio-only] :382-384
-  else { s.null_a = s.null_r = s.null_e = 0; }
+  branch_nulls(s);
   h->R = s.nb * s.B * s.N;
   h->U = h->R;
   // Distinct condition rows.  The CFG branches null whole inputs (FMT.py:360-392): the unconditional branch's current frames all see
@@ -1094,20 +1133,8 @@ int32_t fmt_configure(FmtHandle* h, const FmtPlan* p, void* stream) {
   {
     const bool old_window_plan = h->use_window != 0 && window_eligible(h, p) && !(h->use_window == 3 && flow_eligible(h, p));
     if (h->use_dedup && s.nb > 1 && !old_window_plan) {
-      std::vector<int> urow(h->R), uidx;
-      std::map<std::tuple<int, int, int, int, int, int, int>, int> seen;
-      for (int row = 0; row < h->R; ++row) {
-        const int br = row / (s.B * s.N), b = (row / s.N) % s.B, f = row % s.N;
-        const bool za = (s.null_a >> br) & 1, zr = (s.null_r >> br) & 1, ze = (s.null_e >> br) & 1, ctx = f < s.P;
-        // what cond_gather_kernel reads for this row: (wr source, wa kind, wa clip, wa frame, we kind, we clip, we frame)
-        const int kr = zr ? -1 : b;
-        const int ka = ctx ? 0 : (za ? 1 : 2), kab = (ctx || !za) ? b : -1, kaf = (ctx || !za) ? f : -1;
-        const int ke = ze ? 0 : (s.we_dynamic ? 2 : 1), keb = ze ? -1 : b, kef = (!ze && s.we_dynamic) ? f : -1;
-        const auto key = std::make_tuple(kr, ka, kab, kaf, ke, keb, kef);
-        auto it = seen.find(key);
-        if (it == seen.end()) { it = seen.emplace(key, static_cast<int>(uidx.size())).first; uidx.push_back(row); }
-        urow[row] = it->second;
-      }
+      std::vector<int> urow, uidx;
+      distinct_condition_rows(s, urow, uidx);
       if (static_cast<int>(uidx.size()) < h->R) {
         h->U = static_cast<int>(uidx.size());
         h->dedup = true;

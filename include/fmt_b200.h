@@ -164,6 +164,12 @@ FMT_API int32_t fmt_window_kernel_status(const FmtHandle* h);
 /* With FMT_WIN_TRACE=1 in the environment at fmt_configure: copies the per-CTA barrier stamps of the last window,
  * [cta][barrier][arrive, pass] in SM clocks, into `out` (HOST); returns the element count (call with NULL to size). */
 FMT_API int64_t fmt_debug_window_trace(const FmtHandle* h, int64_t* out, int64_t max_elems);
+/* Host-only (no device work): which token rows (branch, clip, frame) of forward_with_cfv's batched forward (FMT.py:360-392) see the
+ * same condition row [wr | wa | we] - the AdaLN tables hold one row per DISTINCT condition row.  Fills urow[n_branches * batch *
+ * n_frames] (may be NULL) with the distinct-row index of every token row and returns the number of distinct rows, < 0 on bad
+ * arguments. */
+FMT_API int32_t fmt_debug_condition_rows(int32_t n_branches, int32_t batch, int32_t n_frames, int32_t n_prev, int32_t we_dynamic,
+                                         int32_t* urow_out);
 
 /* ---- audio projection in front of the sampler ----
  * Replaces the nn.Sequential(Linear(in_dim, dim_w), LayerNorm(dim_w), SiLU) that FloatApplyAudioProjection runs

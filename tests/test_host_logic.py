@@ -265,3 +265,43 @@ def test_audio_projection_validation_mirrors_reference(pkg):
         node.apply_projection(torch.zeros(1, 10, 9216), layer)
     with pytest.raises(pkg.FmtError):
         node.apply_projection(x, layer)
+
+
+def test_distinct_condition_rows(pkg):
+    """The AdaLN tables hold one row per DISTINCT condition row of forward_with_cfv's batched forward (FMT.py:360-392); this is the
+    host-only view of that map (no GPU): checked against a direct construction of the condition rows from symbolic inputs."""
+    import ctypes as C
+    import numpy as np
+    cabi = sys.modules[pkg.__name__ + "._cabi"]
+    lib = cabi.load_library()
+    N, P = 60, 10
+
+    def reference_map(nb, B, dynamic):
+        # symbolic condition row of (branch, clip, frame): what cat[wr, wa, we] holds, with the per-branch nulling of FMT.py:360-392
+        null = {1: [(0, 0, 0)], 3: [(0, 1, 1), (0, 0, 0), (0, 0, 1)], 4: [(1, 1, 1), (0, 1, 1), (0, 0, 0), (0, 0, 1)]}[nb]   # (zr, za, ze)
+        rows = []
+        for br in range(nb):
+            zr, za, ze = null[br]
+            for b in range(B):
+                for f in range(N):
+                    ctx = f < P
+                    wr = ("wr", b) if not zr else 0
+                    wa = ("prev_wa", b, f) if ctx else (("wa", b, f) if not za else 0)         # prev_wa is never nulled (:366,388)
+                    if ze:
+                        we = 0
+                    elif not dynamic:
+                        we = ("we", b)                                                          # static emotion covers the context frames (:325-326)
+                    else:
+                        we = ("prev_we", b, f) if ctx else ("we", b, f)
+                    rows.append((wr, wa, we))
+        first = {}
+        return [first.setdefault(r, len(first)) for r in rows], len(first)
+
+    for nb, B, dynamic in [(3, 1, 0), (3, 2, 1), (4, 3, 0), (4, 1, 1), (1, 2, 0)]:
+        out = (C.c_int32 * (nb * B * N))()
+        U = lib.fmt_debug_condition_rows(nb, B, N, P, dynamic, out)
+        ref, U_ref = reference_map(nb, B, dynamic)
+        assert U == U_ref and list(out) == ref, (nb, B, dynamic, U, U_ref)
+    assert lib.fmt_debug_condition_rows(3, 1, N, P, 0, None) == 2 * N + 1          # 121 of 180 rows per clip with 3-way CFG
+    assert lib.fmt_debug_condition_rows(1, 4, N, P, 0, None) == 4 * N             # a single branch has nothing to share
+    assert lib.fmt_debug_condition_rows(5, 1, N, P, 0, None) < 0
